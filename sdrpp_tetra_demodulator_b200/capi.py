@@ -1,0 +1,160 @@
+"""ctypes binding of libtdm_b200.so (include/tdm_b200.h).
+
+The shared library is the product; this file only declares its signatures.  Loading
+fails loudly if the library has not been built -- there is no Python or CPU fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+PKG_DIR = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(PKG_DIR, "libtdm_b200.so")
+
+TDM_MAX_TAPS = 65
+TDM_HIST = 64
+TDM_INTERP_PHASES = 128
+TDM_INTERP_TAPS = 8
+TDM_SYNC_BLOCKS = 16
+TDM_STREAM_BUFFER_SIZE = 1000000
+
+TDM_OK = 0
+TDM_ERR_ARG = -1
+TDM_ERR_NO_DEVICE = -2
+TDM_ERR_CUDA = -3
+TDM_ERR_UNSUPPORTED = -4
+TDM_ERR_NOMEM = -5
+
+TDM_MEM_HOST = 0
+TDM_MEM_DEVICE = 1
+
+TDM_OUT_SYMBOLS = 1
+TDM_OUT_DIBITS = 2
+TDM_OUT_BITS = 4
+
+# every symbol include/tdm_b200.h declares (tests check the library exports each one)
+EXPORTED_SYMBOLS = [
+    "tdm_default_config", "tdm_design_from_config", "tdm_create", "tdm_destroy", "tdm_set_stream",
+    "tdm_max_symbols", "tdm_process", "tdm_reset", "tdm_reset_all", "tdm_get_state", "tdm_set_state",
+    "tdm_get_metrics", "tdm_set_config", "tdm_get_design", "tdm_set_kernel_variant", "tdm_last_kernel_ms",
+    "tdm_launch_count", "tdm_pack_dibits", "tdm_synth_capture", "tdm_last_error", "tdm_abi_version",
+]
+
+
+class TdmConfig(C.Structure):
+    """tdm_config: the arguments of dsp::demod::PI4DQPSK::init (src/dsp/pi4dqpsk.h:36)."""
+    _fields_ = [
+        ("symbolrate", C.c_double), ("samplerate", C.c_double),
+        ("rrc_tap_count", C.c_int32), ("reserved0", C.c_int32),
+        ("rrc_beta", C.c_double), ("agc_rate", C.c_double), ("costas_bandwidth", C.c_double),
+        ("fll_bandwidth", C.c_double), ("omega_gain", C.c_double), ("mu_gain", C.c_double),
+        ("omega_rel_limit", C.c_double),
+    ]
+
+
+class TdmDesign(C.Structure):
+    _fields_ = [
+        ("ntaps", C.c_int32), ("reserved0", C.c_int32),
+        ("rrc", C.c_float * TDM_MAX_TAPS), ("be_a", C.c_float * TDM_MAX_TAPS), ("be_b", C.c_float * TDM_MAX_TAPS),
+        ("bank", (C.c_float * TDM_INTERP_TAPS) * TDM_INTERP_PHASES),
+        ("agc_rate", C.c_float), ("agc_set_point", C.c_float), ("agc_max_gain", C.c_float), ("agc_init_gain", C.c_float),
+        ("fll_beta", C.c_float), ("fll_min_freq", C.c_float), ("fll_max_freq", C.c_float), ("fll_init_freq", C.c_float),
+        ("tr_alpha", C.c_float), ("tr_beta", C.c_float), ("tr_min_omega", C.c_float), ("tr_max_omega", C.c_float),
+        ("tr_init_omega", C.c_float),
+        ("costas_alpha", C.c_float), ("costas_beta", C.c_float), ("costas_min_freq", C.c_float),
+        ("costas_max_freq", C.c_float),
+        ("reserved1", C.c_float * 3),
+    ]
+
+
+class TdmSynthParams(C.Structure):
+    _fields_ = [("snr_db", C.c_double), ("max_freq_off_hz", C.c_double), ("min_amp", C.c_double),
+                ("max_amp", C.c_double), ("seed_data", C.c_uint64), ("seed_noise", C.c_uint64)]
+
+
+class TdmMetrics(C.Structure):
+    _fields_ = [("standarderr", C.c_float), ("sync", C.c_uint32), ("n_samples", C.c_uint64),
+                ("n_symbols", C.c_uint64)]
+
+
+# numpy view of tdm_channel_state; itemsize == sizeof(tdm_channel_state) == 720
+STATE_DTYPE = np.dtype([
+    ("agc_gain", "<f4"), ("fll_phase", "<f4"), ("fll_freq", "<f4"), ("tr_mu", "<f4"), ("tr_omega", "<f4"),
+    ("tr_offset", "<i4"), ("costas_phase", "<f4"), ("costas_freq", "<f4"), ("costas_ph2", "<f4"),
+    ("prev_sym", "<u4"), ("err_ptr", "<u4"), ("err_disp", "<u4"), ("err_partial", "<f4"),
+    ("standarderr", "<f4"), ("sync", "<u4"), ("reserved0", "<u4"), ("n_samples", "<u8"), ("n_symbols", "<u8"),
+    ("err_blocks", "<f4", (TDM_SYNC_BLOCKS,)), ("x_hist", "<f4", (2 * TDM_HIST,)),
+    ("r_hist", "<f4", (2 * (TDM_INTERP_TAPS - 1),)), ("reserved1", "<f4", (2,)),
+], align=True)
+METRICS_DTYPE = np.dtype([("standarderr", "<f4"), ("sync", "<u4"), ("n_samples", "<u8"), ("n_symbols", "<u8")],
+                         align=True)
+
+
+class TdmError(RuntimeError):
+    def __init__(self, code: int, where: str, text: str):
+        super().__init__(f"{where} failed with tdm_status {code}: {text}")
+        self.code = code
+
+
+_LIB = None
+
+
+def lib() -> C.CDLL:
+    """Load libtdm_b200.so.  Raises if it is missing: the CUDA library IS the product."""
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            f"or `make -C {os.path.join(PKG_DIR, 'csrc')}` (needs nvcc; there is no CPU fallback)")
+    L = C.CDLL(LIB_PATH)
+    vp, i32, i64, u32 = C.c_void_p, C.c_int32, C.c_int64, C.c_uint32
+    sig = {
+        "tdm_default_config": (C.c_int, [C.POINTER(TdmConfig)]),
+        "tdm_design_from_config": (C.c_int, [C.POINTER(TdmConfig), C.POINTER(TdmDesign)]),
+        "tdm_create": (C.c_int, [C.POINTER(TdmConfig), i32, i32, i32, C.POINTER(vp)]),
+        "tdm_destroy": (C.c_int, [vp]),
+        "tdm_set_stream": (C.c_int, [vp, vp]),
+        "tdm_max_symbols": (i64, [vp, i64]),
+        "tdm_process": (C.c_int, [vp, vp, i64, i32, vp, vp, vp, i64, vp, u32, i32]),
+        "tdm_reset": (C.c_int, [vp]),
+        "tdm_reset_all": (C.c_int, [vp]),
+        "tdm_get_state": (C.c_int, [vp, vp, i32]),
+        "tdm_set_state": (C.c_int, [vp, vp, i32]),
+        "tdm_get_metrics": (C.c_int, [vp, vp, i32]),
+        "tdm_set_config": (C.c_int, [vp, C.POINTER(TdmConfig)]),
+        "tdm_get_design": (C.c_int, [vp, C.POINTER(TdmDesign)]),
+        "tdm_set_kernel_variant": (C.c_int, [vp, i32]),
+        "tdm_last_kernel_ms": (C.c_int, [vp, C.POINTER(C.c_float)]),
+        "tdm_launch_count": (i64, [vp]),
+        "tdm_pack_dibits": (C.c_int, [vp, vp, i64, vp, vp, i64]),
+        "tdm_synth_capture": (C.c_int, [i32, vp, C.POINTER(TdmSynthParams), i32, i64, i64, i32, vp, vp, i64]),
+        "tdm_last_error": (C.c_char_p, []),
+        "tdm_abi_version": (C.c_int, []),
+    }
+    for name, (res, args) in sig.items():
+        fn = getattr(L, name)
+        fn.restype = res
+        fn.argtypes = args
+    _LIB = L
+    return L
+
+
+def check(rc: int, where: str) -> None:
+    if rc != TDM_OK:
+        raise TdmError(rc, where, lib().tdm_last_error().decode(errors="replace"))
+
+
+def default_config() -> TdmConfig:
+    cfg = TdmConfig()
+    check(lib().tdm_default_config(C.byref(cfg)), "tdm_default_config")
+    return cfg
+
+
+def design_from_config(cfg: TdmConfig) -> TdmDesign:
+    d = TdmDesign()
+    check(lib().tdm_design_from_config(C.byref(cfg), C.byref(d)), "tdm_design_from_config")
+    return d

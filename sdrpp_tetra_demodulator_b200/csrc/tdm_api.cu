@@ -1,0 +1,385 @@
+// tdm_api.cu -- the extern "C" ABI of libtdm_b200.so (declared in include/tdm_b200.h).
+//
+// Thin by design: argument checking, device-memory ownership, host<->device staging for
+// callers that hand in host buffers, and kernel launches.  There is NO CPU fallback: if
+// no usable sm_100 device is present tdm_create fails with TDM_ERR_NO_DEVICE, and nothing
+// in this library computes demodulator outputs on the host.
+#include <cuda_runtime.h>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <vector>
+#include "tdm_b200.h"
+#include "tdm_kernels.cuh"
+
+namespace {
+
+thread_local char g_err[512] = "";
+
+int fail(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+#define TDM_CUDA(expr)                                                                              \
+    do {                                                                                            \
+        cudaError_t e__ = (expr);                                                                   \
+        if (e__ != cudaSuccess) { return fail(TDM_ERR_CUDA, "%s: %s", #expr, cudaGetErrorString(e__)); } \
+    } while (0)
+
+struct DeviceGuard {
+    int prev = -1;
+    explicit DeviceGuard(int dev) {
+        cudaGetDevice(&prev);
+        if (prev != dev) { cudaSetDevice(dev); }
+        else { prev = -1; }
+    }
+    ~DeviceGuard() {
+        if (prev >= 0) { cudaSetDevice(prev); }
+    }
+};
+
+}  // namespace
+
+struct tdm_handle {
+    int device = 0;
+    int n_channels = 0;
+    int max_chunk = 0;
+    long long max_syms = 0;             // per-channel output stride of the staging buffers
+    tdm_config cfg{};
+    tdm_design design{};
+    cudaStream_t own_stream = nullptr;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev_start = nullptr, ev_stop = nullptr;
+    int variant = 0;
+    long long launches = 0;
+    // device memory owned by the handle
+    float* d_bank = nullptr;
+    tdm_channel_state* d_states = nullptr;
+    // staging for TDM_MEM_HOST callers (allocated lazily)
+    float2* d_iq = nullptr;
+    float2* d_syms = nullptr;
+    uint8_t* d_dibits = nullptr;
+    uint8_t* d_bits = nullptr;
+    int* d_counts = nullptr;
+};
+
+namespace {
+
+void fill_params(const tdm_handle* h, tdm::DemodParams& p) {
+    const tdm_design& d = h->design;
+    std::memcpy(p.be_a, d.be_a, sizeof(p.be_a));
+    std::memcpy(p.be_b, d.be_b, sizeof(p.be_b));
+    std::memcpy(p.rrc, d.rrc, sizeof(p.rrc));
+    p.agc_rate = d.agc_rate; p.agc_set_point = d.agc_set_point; p.agc_max_gain = d.agc_max_gain;
+    p.fll_beta = d.fll_beta; p.fll_min_freq = d.fll_min_freq; p.fll_max_freq = d.fll_max_freq;
+    p.tr_alpha = d.tr_alpha; p.tr_beta = d.tr_beta; p.tr_min_omega = d.tr_min_omega; p.tr_max_omega = d.tr_max_omega;
+    p.costas_alpha = d.costas_alpha; p.costas_beta = d.costas_beta;
+    p.costas_min_freq = d.costas_min_freq; p.costas_max_freq = d.costas_max_freq;
+    p.bank = h->d_bank;
+    p.n_channels = h->n_channels;
+    p.states = h->d_states;
+}
+
+void init_state(const tdm_design& d, tdm_channel_state& s) {
+    std::memset(&s, 0, sizeof(s));
+    s.agc_gain = d.agc_init_gain;       // FastAGC::_gain = initGain [A.3]
+    s.fll_freq = d.fll_init_freq;       // pcl.init(..., initFreq, ...) fll.cpp:26
+    s.tr_omega = d.tr_init_omega;       // pcl.init(..., _omega, ...) complex_fd.cpp:22
+}
+
+long long max_symbols_for(const tdm_design& d, long long count) {
+    // Every symbol advances the read offset by floor(mu) with mu' = mu + omega + alpha*e,
+    // |e| <= 1, omega >= tr_min_omega: K symbols consume >= K*(omega_min - |alpha|) - 1 samples.
+    double step = (double)d.tr_min_omega - (double)(d.tr_alpha < 0 ? -d.tr_alpha : d.tr_alpha);
+    if (step < 1.0) { step = 1.0; }
+    long long k = (long long)((double)(count + 1) / step) + 2;
+    return (k + 15) & ~15LL;
+}
+
+int upload_design(tdm_handle* h) {
+    TDM_CUDA(cudaMemcpyAsync(h->d_bank, h->design.bank, sizeof(h->design.bank), cudaMemcpyHostToDevice, h->stream));
+    TDM_CUDA(cudaStreamSynchronize(h->stream));
+    return TDM_OK;
+}
+
+int ensure_staging(tdm_handle* h, uint32_t flags) {
+    const size_t C = (size_t)h->n_channels;
+    if (!h->d_iq) { TDM_CUDA(cudaMalloc(&h->d_iq, sizeof(float2) * C * (size_t)h->max_chunk)); }
+    if (!h->d_counts) { TDM_CUDA(cudaMalloc(&h->d_counts, sizeof(int) * C)); }
+    if ((flags & TDM_OUT_SYMBOLS) && !h->d_syms) { TDM_CUDA(cudaMalloc(&h->d_syms, sizeof(float2) * C * (size_t)h->max_syms)); }
+    if ((flags & TDM_OUT_DIBITS) && !h->d_dibits) { TDM_CUDA(cudaMalloc(&h->d_dibits, C * (size_t)h->max_syms)); }
+    if ((flags & TDM_OUT_BITS) && !h->d_bits) { TDM_CUDA(cudaMalloc(&h->d_bits, 2 * C * (size_t)h->max_syms)); }
+    return TDM_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* tdm_last_error(void) { return g_err; }
+int tdm_abi_version(void) { return TDM_ABI_VERSION; }
+
+int tdm_create(const tdm_config* cfg, int32_t n_channels, int32_t max_chunk, int32_t device, tdm_handle** out) {
+    if (!out) { return fail(TDM_ERR_ARG, "tdm_create: out is null"); }
+    *out = nullptr;
+    if (n_channels <= 0 || max_chunk <= 0) { return fail(TDM_ERR_ARG, "tdm_create: n_channels and max_chunk must be > 0"); }
+    tdm_config local;
+    if (!cfg) { tdm_default_config(&local); cfg = &local; }
+    tdm_design design;
+    int rc = tdm_design_from_config(cfg, &design);
+    if (rc != TDM_OK) { return fail(rc, "tdm_create: configuration not supported (rrc_tap_count must be 1..%d)", TDM_MAX_TAPS); }
+
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) {
+        return fail(TDM_ERR_NO_DEVICE, "tdm_create: no CUDA device (this library has no CPU fallback)");
+    }
+    if (device < 0 || device >= ndev) { return fail(TDM_ERR_ARG, "tdm_create: device %d out of range (%d devices)", device, ndev); }
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) { return fail(TDM_ERR_NO_DEVICE, "tdm_create: cannot query device %d", device); }
+    if (prop.major != 10) {
+        return fail(TDM_ERR_NO_DEVICE, "tdm_create: device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor);
+    }
+
+    tdm_handle* h = new (std::nothrow) tdm_handle();
+    if (!h) { return fail(TDM_ERR_NOMEM, "tdm_create: out of host memory"); }
+    h->device = device;
+    h->n_channels = n_channels;
+    h->max_chunk = max_chunk;
+    h->cfg = *cfg;
+    h->design = design;
+    h->max_syms = max_symbols_for(design, max_chunk);
+    DeviceGuard guard(device);
+    auto cleanup = [&](int code) { tdm_destroy(h); return code; };
+    if (cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking) != cudaSuccess) { return cleanup(fail(TDM_ERR_CUDA, "cudaStreamCreate failed")); }
+    h->stream = h->own_stream;
+    if (cudaEventCreate(&h->ev_start) != cudaSuccess || cudaEventCreate(&h->ev_stop) != cudaSuccess) { return cleanup(fail(TDM_ERR_CUDA, "cudaEventCreate failed")); }
+    if (cudaMalloc(&h->d_bank, sizeof(design.bank)) != cudaSuccess) { return cleanup(fail(TDM_ERR_NOMEM, "cudaMalloc(bank) failed")); }
+    if (cudaMalloc(&h->d_states, sizeof(tdm_channel_state) * (size_t)n_channels) != cudaSuccess) { return cleanup(fail(TDM_ERR_NOMEM, "cudaMalloc(states) failed")); }
+    rc = upload_design(h);
+    if (rc != TDM_OK) { return cleanup(rc); }
+    rc = tdm_reset_all(h);
+    if (rc != TDM_OK) { return cleanup(rc); }
+    *out = h;
+    return TDM_OK;
+}
+
+int tdm_destroy(tdm_handle* h) {
+    if (!h) { return TDM_OK; }
+    DeviceGuard guard(h->device);
+    if (h->own_stream) { cudaStreamSynchronize(h->own_stream); }
+    cudaFree(h->d_bank); cudaFree(h->d_states); cudaFree(h->d_iq); cudaFree(h->d_syms);
+    cudaFree(h->d_dibits); cudaFree(h->d_bits); cudaFree(h->d_counts);
+    if (h->ev_start) { cudaEventDestroy(h->ev_start); }
+    if (h->ev_stop) { cudaEventDestroy(h->ev_stop); }
+    if (h->own_stream) { cudaStreamDestroy(h->own_stream); }
+    delete h;
+    return TDM_OK;
+}
+
+int tdm_set_stream(tdm_handle* h, void* cuda_stream) {
+    if (!h) { return fail(TDM_ERR_ARG, "null handle"); }
+    h->stream = cuda_stream ? (cudaStream_t)cuda_stream : h->own_stream;
+    return TDM_OK;
+}
+
+int64_t tdm_max_symbols(const tdm_handle* h, int64_t count) {
+    if (!h || count < 0) { return TDM_ERR_ARG; }
+    return max_symbols_for(h->design, count);
+}
+
+int tdm_process(tdm_handle* h, const float* iq, int64_t in_stride, int32_t count, float* syms, uint8_t* dibits,
+                uint8_t* bits, int64_t out_stride, int32_t* out_counts, uint32_t out_flags, int32_t mem_kind) {
+    if (!h) { return fail(TDM_ERR_ARG, "tdm_process: null handle"); }
+    if (count < 0) { return fail(TDM_ERR_ARG, "tdm_process: negative count"); }
+    if (!out_counts) { return fail(TDM_ERR_ARG, "tdm_process: out_counts is null"); }
+    if (count > 0 && !iq) { return fail(TDM_ERR_ARG, "tdm_process: iq is null"); }
+    if (in_stride < count) { return fail(TDM_ERR_ARG, "tdm_process: in_stride < count"); }
+    if (((out_flags & TDM_OUT_SYMBOLS) && !syms) || ((out_flags & TDM_OUT_DIBITS) && !dibits) || ((out_flags & TDM_OUT_BITS) && !bits)) {
+        return fail(TDM_ERR_ARG, "tdm_process: an output selected in out_flags has a null buffer");
+    }
+    const long long need = max_symbols_for(h->design, count);
+    if ((out_flags & (TDM_OUT_SYMBOLS | TDM_OUT_DIBITS | TDM_OUT_BITS)) && out_stride < need) {
+        return fail(TDM_ERR_ARG, "tdm_process: out_stride %lld < tdm_max_symbols(count) = %lld", (long long)out_stride, need);
+    }
+    DeviceGuard guard(h->device);
+    const size_t C = (size_t)h->n_channels;
+
+    tdm::DemodParams p;
+    fill_params(h, p);
+    p.count = count;
+
+    if (mem_kind == TDM_MEM_DEVICE) {
+        p.iq = reinterpret_cast<const float2*>(iq);
+        p.in_stride = in_stride;
+        p.syms = (out_flags & TDM_OUT_SYMBOLS) ? reinterpret_cast<float2*>(syms) : nullptr;
+        p.dibits = (out_flags & TDM_OUT_DIBITS) ? dibits : nullptr;
+        p.bits = (out_flags & TDM_OUT_BITS) ? bits : nullptr;
+        p.out_stride = out_stride;
+        p.out_counts = out_counts;
+        TDM_CUDA(cudaEventRecord(h->ev_start, h->stream));
+        const int n = tdm::launch_demod(p, h->variant, h->stream);
+        if (n < 0) { return fail(TDM_ERR_CUDA, "demod kernel launch failed: %s", cudaGetErrorString(cudaGetLastError())); }
+        h->launches += n;
+        TDM_CUDA(cudaEventRecord(h->ev_stop, h->stream));
+        return TDM_OK;
+    }
+    if (mem_kind != TDM_MEM_HOST) { return fail(TDM_ERR_ARG, "tdm_process: unknown mem_kind %d", mem_kind); }
+    if (count > h->max_chunk) { return fail(TDM_ERR_ARG, "tdm_process: count %d > max_chunk %d given to tdm_create", count, h->max_chunk); }
+
+    int rc = ensure_staging(h, out_flags);
+    if (rc != TDM_OK) { return rc; }
+    const long long dstride = h->max_syms;      // staging rows are max_syms wide
+    if (count > 0) {
+        TDM_CUDA(cudaMemcpy2DAsync(h->d_iq, sizeof(float2) * (size_t)count, iq, sizeof(float2) * (size_t)in_stride,
+                                   sizeof(float2) * (size_t)count, C, cudaMemcpyHostToDevice, h->stream));
+    }
+    p.iq = h->d_iq;
+    p.in_stride = count;
+    p.syms = (out_flags & TDM_OUT_SYMBOLS) ? h->d_syms : nullptr;
+    p.dibits = (out_flags & TDM_OUT_DIBITS) ? h->d_dibits : nullptr;
+    p.bits = (out_flags & TDM_OUT_BITS) ? h->d_bits : nullptr;
+    p.out_stride = dstride;
+    p.out_counts = h->d_counts;
+    TDM_CUDA(cudaEventRecord(h->ev_start, h->stream));
+    const int n = tdm::launch_demod(p, h->variant, h->stream);
+    if (n < 0) { return fail(TDM_ERR_CUDA, "demod kernel launch failed: %s", cudaGetErrorString(cudaGetLastError())); }
+    h->launches += n;
+    TDM_CUDA(cudaEventRecord(h->ev_stop, h->stream));
+    // Only the part of each row a call of `count` samples can fill is copied back.
+    const size_t w = (size_t)need;
+    if (out_flags & TDM_OUT_SYMBOLS) {
+        TDM_CUDA(cudaMemcpy2DAsync(syms, sizeof(float2) * (size_t)out_stride, h->d_syms, sizeof(float2) * (size_t)dstride,
+                                   sizeof(float2) * w, C, cudaMemcpyDeviceToHost, h->stream));
+    }
+    if (out_flags & TDM_OUT_DIBITS) {
+        TDM_CUDA(cudaMemcpy2DAsync(dibits, (size_t)out_stride, h->d_dibits, (size_t)dstride, w, C, cudaMemcpyDeviceToHost, h->stream));
+    }
+    if (out_flags & TDM_OUT_BITS) {
+        TDM_CUDA(cudaMemcpy2DAsync(bits, 2 * (size_t)out_stride, h->d_bits, 2 * (size_t)dstride, 2 * w, C, cudaMemcpyDeviceToHost, h->stream));
+    }
+    TDM_CUDA(cudaMemcpyAsync(out_counts, h->d_counts, sizeof(int) * C, cudaMemcpyDeviceToHost, h->stream));
+    TDM_CUDA(cudaStreamSynchronize(h->stream));
+    return TDM_OK;
+}
+
+int tdm_get_state(tdm_handle* h, tdm_channel_state* host_states, int32_t n_channels) {
+    if (!h || !host_states || n_channels != h->n_channels) { return fail(TDM_ERR_ARG, "tdm_get_state: bad arguments"); }
+    DeviceGuard guard(h->device);
+    TDM_CUDA(cudaMemcpyAsync(host_states, h->d_states, sizeof(tdm_channel_state) * (size_t)n_channels, cudaMemcpyDeviceToHost, h->stream));
+    TDM_CUDA(cudaStreamSynchronize(h->stream));
+    return TDM_OK;
+}
+
+int tdm_set_state(tdm_handle* h, const tdm_channel_state* host_states, int32_t n_channels) {
+    if (!h || !host_states || n_channels != h->n_channels) { return fail(TDM_ERR_ARG, "tdm_set_state: bad arguments"); }
+    DeviceGuard guard(h->device);
+    TDM_CUDA(cudaMemcpyAsync(h->d_states, host_states, sizeof(tdm_channel_state) * (size_t)n_channels, cudaMemcpyHostToDevice, h->stream));
+    TDM_CUDA(cudaStreamSynchronize(h->stream));
+    return TDM_OK;
+}
+
+int tdm_reset_all(tdm_handle* h) {
+    if (!h) { return fail(TDM_ERR_ARG, "null handle"); }
+    std::vector<tdm_channel_state> st((size_t)h->n_channels);
+    for (auto& s : st) { init_state(h->design, s); }
+    return tdm_set_state(h, st.data(), h->n_channels);
+}
+
+// PI4DQPSK::reset (pi4dqpsk.cpp:120-130) = fll.reset (phase 0, freq initFreq; fll.cpp:120-127),
+// rrc.reset (FIR history cleared, [A.4]), agc.reset (gain = initGain), costas.reset (phase/freq
+// back to their initial values, ph2 untouched), recov.reset (offset 0, mu 0, omega init;
+// complex_fd.cpp:78-87).  One deliberate difference, forced by the shared delay line: the
+// reference clears only the RRC FIR's history and keeps the two band-edge FIRs'; here the
+// single line behind all three is cleared (DESIGN.md "reset").
+int tdm_reset(tdm_handle* h) {
+    if (!h) { return fail(TDM_ERR_ARG, "null handle"); }
+    std::vector<tdm_channel_state> st((size_t)h->n_channels);
+    int rc = tdm_get_state(h, st.data(), h->n_channels);
+    if (rc != TDM_OK) { return rc; }
+    for (auto& s : st) {
+        s.fll_phase = 0; s.fll_freq = h->design.fll_init_freq;
+        std::memset(s.x_hist, 0, sizeof(s.x_hist));
+        s.agc_gain = h->design.agc_init_gain;
+        s.costas_phase = 0; s.costas_freq = 0;
+        s.tr_offset = 0; s.tr_mu = 0; s.tr_omega = h->design.tr_init_omega;
+    }
+    return tdm_set_state(h, st.data(), h->n_channels);
+}
+
+int tdm_get_metrics(tdm_handle* h, tdm_metrics* m, int32_t n_channels) {
+    if (!h || !m || n_channels != h->n_channels) { return fail(TDM_ERR_ARG, "tdm_get_metrics: bad arguments"); }
+    std::vector<tdm_channel_state> st((size_t)n_channels);
+    int rc = tdm_get_state(h, st.data(), n_channels);
+    if (rc != TDM_OK) { return rc; }
+    for (int c = 0; c < n_channels; ++c) {
+        m[c].standarderr = st[c].standarderr; m[c].sync = st[c].sync;
+        m[c].n_samples = st[c].n_samples; m[c].n_symbols = st[c].n_symbols;
+    }
+    return TDM_OK;
+}
+
+int tdm_set_config(tdm_handle* h, const tdm_config* cfg) {
+    if (!h || !cfg) { return fail(TDM_ERR_ARG, "tdm_set_config: bad arguments"); }
+    tdm_design d;
+    int rc = tdm_design_from_config(cfg, &d);
+    if (rc != TDM_OK) { return fail(rc, "tdm_set_config: configuration not supported"); }
+    DeviceGuard guard(h->device);
+    TDM_CUDA(cudaStreamSynchronize(h->stream));
+    h->cfg = *cfg;
+    h->design = d;
+    h->max_syms = max_symbols_for(d, h->max_chunk);
+    // staging sized from the old design may be too small now: drop it, it is re-made lazily
+    cudaFree(h->d_syms); cudaFree(h->d_dibits); cudaFree(h->d_bits);
+    h->d_syms = nullptr; h->d_dibits = nullptr; h->d_bits = nullptr;
+    return upload_design(h);
+}
+
+int tdm_get_design(const tdm_handle* h, tdm_design* out) {
+    if (!h || !out) { return fail(TDM_ERR_ARG, "tdm_get_design: bad arguments"); }
+    *out = h->design;
+    return TDM_OK;
+}
+
+int tdm_set_kernel_variant(tdm_handle* h, int32_t variant) {
+    if (!h || variant < 0) { return fail(TDM_ERR_ARG, "tdm_set_kernel_variant: bad arguments"); }
+    h->variant = variant;
+    return TDM_OK;
+}
+
+int tdm_last_kernel_ms(tdm_handle* h, float* ms) {
+    if (!h || !ms) { return fail(TDM_ERR_ARG, "tdm_last_kernel_ms: bad arguments"); }
+    DeviceGuard guard(h->device);
+    TDM_CUDA(cudaEventSynchronize(h->ev_stop));
+    TDM_CUDA(cudaEventElapsedTime(ms, h->ev_start, h->ev_stop));
+    return TDM_OK;
+}
+
+int64_t tdm_launch_count(const tdm_handle* h) { return h ? h->launches : 0; }
+
+int tdm_pack_dibits(tdm_handle* h, const uint8_t* dibits, int64_t in_stride, const int32_t* counts, uint8_t* packed,
+                    int64_t out_stride) {
+    if (!h || !dibits || !counts || !packed) { return fail(TDM_ERR_ARG, "tdm_pack_dibits: bad arguments"); }
+    if (out_stride * 4 < in_stride) { return fail(TDM_ERR_ARG, "tdm_pack_dibits: out_stride too small"); }
+    DeviceGuard guard(h->device);
+    const int n = tdm::launch_pack_dibits(dibits, in_stride, counts, packed, out_stride, h->n_channels, in_stride, h->stream);
+    if (n < 0) { return fail(TDM_ERR_CUDA, "pack kernel launch failed"); }
+    h->launches += n;
+    return TDM_OK;
+}
+
+int tdm_synth_capture(int32_t device, void* cuda_stream, const tdm_synth_params* p, int32_t n_channels, int64_t n_samples,
+                      int64_t stride, int32_t first_channel, float* iq_dev, uint8_t* tx_dibits_dev, int64_t tx_stride) {
+    if (!p || !iq_dev || n_channels <= 0 || n_samples <= 0 || stride < n_samples) { return fail(TDM_ERR_ARG, "tdm_synth_capture: bad arguments"); }
+    DeviceGuard guard(device);
+    const int n = tdm::launch_synth(*p, n_channels, n_samples, stride, first_channel, reinterpret_cast<float2*>(iq_dev),
+                                    tx_dibits_dev, tx_stride, (cudaStream_t)cuda_stream);
+    if (n < 0) { return fail(TDM_ERR_CUDA, "synth kernel launch failed: %s", cudaGetErrorString(cudaGetLastError())); }
+    return TDM_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,397 @@
+// tdm_kernels.cu -- the fused pi/4-DQPSK demodulation kernel for sm_100a.
+//
+// One launch runs the WHOLE reference chain for `count` samples of every channel:
+//   FastAGC -> band-edge FLL -> RRC matched filter -> ML timing recovery -> pi/4 Costas
+//   -> slicer + differential decoder -> (optional) bit unpack
+// i.e. dsp::demod::PI4DQPSK::process (src/dsp/pi4dqpsk.cpp:132-140), then
+// DQPSKSymbolExtractor::process (src/dsp/dqpsk_sym_extr.cpp:4-55) and
+// BitUnpacker::process (src/dsp/bit_unpacker.cpp:4-10), with the per-channel state
+// the reference keeps in class members carried in tdm_channel_state.
+//
+// Mapping (variant "tpc<T>"): one thread per channel, time processed in blocks of T
+// samples.  The chain is a strict recurrence at sample rate (AGC gain, FLL phase) and
+// at symbol rate (timing, Costas), so time cannot be split; what CAN be hoisted out of
+// the recurrence is almost all of the FIR work:
+//   * lbe/hbe/RRC all filter the same FLL-output sequence x (fll.cpp:141-142 ->
+//     pi4dqpsk.cpp:135-136), so ONE 64-deep delay line (shared memory, [entry][lane] so
+//     a warp's accesses are conflict-free) feeds all three;
+//   * the band-edge taps are exact conjugates (fll.cpp:89-93): hbe = P + jQ, lbe = P - jQ
+//     with P = sum a_k x, Q = sum b_k x  ->  6 real chains per output instead of 10;
+//   * for a block of T outputs the contributions of the 64 samples older than the block
+//     ("old part") do not depend on the block's own feedback: they are accumulated first,
+//     each history sample loaded once from shared memory and used for up to T outputs
+//     x 6 chains, taps as constant-bank FFMA operands.  Only the last <= T terms of each
+//     chain sit inside the serial loop.
+// Every chain still adds its terms in ascending tap order with one fma per term, which
+// is the canonical order the CPU checker follows -- the blocking changes WHEN a term is
+// added, never the order within a chain.
+#include "tdm_kernels.cuh"
+#include "tdm_math.cuh"
+#include <cstdio>
+
+namespace tdm {
+
+namespace {
+
+constexpr int kHist = TDM_HIST;            // 64
+constexpr int kTaps = TDM_MAX_TAPS;        // 65
+constexpr int kITaps = TDM_INTERP_TAPS;    // 8
+constexpr int kIPhases = TDM_INTERP_PHASES;
+
+template <int T>
+struct TpcLayout {
+    static_assert(kHist % T == 0, "block length must divide the history length");
+    static constexpr int kSlots = kHist / T + 1;         // ring of (64/T + 1) blocks of T
+    static constexpr int kXEntries = kSlots * T;
+    static constexpr int kREntries = (T + kITaps - 1 <= 16) ? 16 : 32;   // RRC-output ring (power of 2)
+    static constexpr int kWarpFloat2 = (kXEntries + kREntries) * 32;
+    static constexpr size_t kWarpBytes = sizeof(float2) * kWarpFloat2;
+};
+
+struct SymbolState {
+    float mu, om;
+    int offset;
+    float cph, cfr, ph2;
+    uint32_t prev;
+    uint32_t err_ptr, err_disp;
+    float err_partial, standarderr;
+    uint32_t sync;
+    int nsym;
+};
+
+// One output symbol: interpolate at `offset`, timing-error update, Costas, slice, decode.
+// complex_fd.cpp:96-143, pi4dqpsk_costas.cpp:5-28, dqpsk_sym_extr.cpp:4-55, bit_unpacker.cpp:6-7.
+template <int RE>
+__device__ __forceinline__ void do_symbol(const DemodParams& p, const float* __restrict__ bank_s,
+                                          const float2* __restrict__ rs, int lane, SymbolState& st,
+                                          float* __restrict__ err_blocks, bool active, long long out_base) {
+    // --- polyphase interpolation + derivative
+    // phase = clamp(floor(mu*128), 0, 127) (complex_fd.cpp:101).  The clamp is done on the float and the
+    // edge cases below are folded into one expression on purpose: with an integer min/max clamp followed
+    // by `if (ph == 0) .. else if (ph == 127) ..`, ptxas 12.9 for sm_100a derived the `ph == 127` test from
+    // the predicate output of VIMNMX.RELU and took the last-phase branch for ph == 0 (seen on hardware).
+    const float phf = fminf(fmaxf(floorf(mul_rn(st.mu, (float)kIPhases)), 0.0f), (float)(kIPhases - 1));
+    const int ph = (int)phf;
+    const int plo = max(ph - 1, 0);
+    const int phi = min(ph + 1, kIPhases - 1);
+    const float4* r0 = reinterpret_cast<const float4*>(bank_s + ph * kITaps);
+    const float4* r1 = reinterpret_cast<const float4*>(bank_s + phi * kITaps);
+    const float4* r2 = reinterpret_cast<const float4*>(bank_s + plo * kITaps);
+    float t0[8], t1[8], t2[8];
+    *reinterpret_cast<float4*>(&t0[0]) = r0[0]; *reinterpret_cast<float4*>(&t0[4]) = r0[1];
+    *reinterpret_cast<float4*>(&t1[0]) = r1[0]; *reinterpret_cast<float4*>(&t1[4]) = r1[1];
+    *reinterpret_cast<float4*>(&t2[0]) = r2[0]; *reinterpret_cast<float4*>(&t2[4]) = r2[1];
+    float yre = 0.f, yim = 0.f, are = 0.f, aim = 0.f, bre = 0.f, bim = 0.f;
+#pragma unroll
+    for (int k = 0; k < kITaps; ++k) {
+        // RRC outputs offset-7 .. offset live at linear ring index offset+k (7 history entries first)
+        const float2 v = rs[((st.offset + k) & (RE - 1)) * 32 + lane];
+        yre = fma_rn(t0[k], v.x, yre); yim = fma_rn(t0[k], v.y, yim);
+        are = fma_rn(t1[k], v.x, are); aim = fma_rn(t1[k], v.y, aim);
+        bre = fma_rn(t2[k], v.x, bre); bim = fma_rn(t2[k], v.y, bim);
+    }
+    // derivative (complex_fd.cpp:107-123): first phase fT1 - y, last phase y - fT_1, otherwise
+    // (fT1 - fT_1) * 0.5.  At the edges the clamped neighbour row IS the centre row, so its dot product
+    // equals y bit for bit and all three cases are (a - b) * scale with scale 1 or 0.5 (x1 is exact).
+    const float dscale = (phi - plo == 2) ? 0.5f : 1.0f;
+    const float dre = mul_rn(sub_rn(are, bre), dscale);
+    const float dim = mul_rn(sub_rn(aim, bim), dscale);
+    float terr = add_rn(yre > 0.f ? dre : -dre, yim > 0.f ? dim : -dim);
+    terr = clampf(terr, -1.0f, 1.0f);
+#ifdef TDM_DEBUG_TRACE
+    if (out_base == 0 && st.nsym >= 10 && st.nsym < 22) {
+        printf("sym %d off %d ph %d y=(%g,%g) a=(%g,%g) b=(%g,%g) d=(%g,%g) terr=%g om=%g mu=%g alpha=%g beta=%g t0=%g,%g t1=%g,%g\n", st.nsym, st.offset, ph,
+               yre, yim, are, aim, bre, bim, dre, dim, terr, st.om, st.mu, p.tr_alpha, p.tr_beta, t0[3], t0[4], t1[3], t1[4]);
+    }
+#endif
+    st.om = clampf(fma_rn(p.tr_beta, terr, st.om), p.tr_min_omega, p.tr_max_omega);
+    st.mu = add_rn(st.mu, fma_rn(p.tr_alpha, terr, st.om));
+    const float delta = floorf(st.mu);
+    st.offset += (int)delta;
+    st.mu = sub_rn(st.mu, delta);
+
+    // --- pi/4 Costas
+    float sn, cs;
+    sincos_canon(st.cph, sn, cs);
+    const float zr = fma_rn(yre, cs, mul_rn(yim, sn));
+    const float zi = fma_rn(yim, cs, -mul_rn(yre, sn));
+    const float two_pi_c = 2 * TDM_FL_M_PI;
+    st.ph2 = add_rn(st.ph2, -(TDM_FL_M_PI / 4.0f));
+    if (st.ph2 >= two_pi_c) { st.ph2 = sub_rn(st.ph2, two_pi_c); }
+    else if (st.ph2 <= -two_pi_c) { st.ph2 = add_rn(st.ph2, two_pi_c); }
+    float s2, c2;
+    sincos_canon(st.ph2, s2, c2);
+    const float ur = fma_rn(zr, c2, -mul_rn(zi, s2));
+    const float ui = fma_rn(zi, c2, mul_rn(zr, s2));
+    float cerr = sub_rn(ur > 0.f ? ui : -ui, ui > 0.f ? ur : -ur);
+    cerr = clampf(cerr, -1.0f, 1.0f);
+    st.cfr = clampf(fma_rn(p.costas_beta, cerr, st.cfr), p.costas_min_freq, p.costas_max_freq);
+    st.cph = wrap_pi(add_rn(st.cph, fma_rn(p.costas_alpha, cerr, st.cfr)));
+
+    // --- slicer, sync metric, differential decode
+    const bool a = ui < 0.f, b = ur < 0.f;
+    const float ideal = a ? (b ? -2.35619449f : -0.785398185f) : (b ? 2.35619449f : 0.785398185f);
+    const float dist = fabsf(sub_rn(ideal, atan2f(ui, ur)));
+    st.err_partial = add_rn(st.err_partial, dist);
+    st.err_ptr++;
+    st.err_disp++;
+    if (st.err_disp >= TDM_SYNC_DISPLAY) {
+        err_blocks[(st.err_ptr - 1) / TDM_SYNC_DISPLAY] = st.err_partial;
+        st.err_partial = 0.f;
+        float tot = 0.f;
+#pragma unroll
+        for (int j = 0; j < TDM_SYNC_BLOCKS; ++j) { tot = add_rn(tot, err_blocks[j]); }
+        st.standarderr = __fdiv_rn(tot, (float)TDM_SYNC_BUF);
+        st.sync = st.standarderr < 0.35f ? 1u : 0u;
+        st.err_disp = 0;
+    }
+    if (st.err_ptr >= TDM_SYNC_BUF) { st.err_ptr = 0; }
+    const uint32_t sym = ((uint32_t)a << 1) | (uint32_t)(a != b);
+    const uint32_t pd = (sym - st.prev + 4u) & 3u;
+    const uint32_t db = pd ^ (pd >> 1);          // 0,1,2,3 -> 0,1,3,2
+    st.prev = sym;
+    if (active && st.nsym < p.out_stride) {   // rows are sized by tdm_max_symbols(); never write past one
+        const long long o = out_base + st.nsym;
+        if (p.syms) { p.syms[o] = make_float2(ur, ui); }
+        if (p.dibits) { p.dibits[o] = (uint8_t)db; }
+        if (p.bits) { reinterpret_cast<uchar2*>(p.bits)[o] = make_uchar2((uint8_t)((db >> 1) & 1u), (uint8_t)(db & 1u)); }
+    }
+    st.nsym++;
+}
+
+// ---------------------------------------------------------------------------------------
+// Variant tpc<T>: thread per channel, one warp per CTA (so consecutive warps land on
+// different SMs and each gets a whole SM's issue slots and shared-memory bandwidth).
+// ---------------------------------------------------------------------------------------
+template <int T>
+__global__ void __launch_bounds__(128) demod_tpc_kernel(const __grid_constant__ DemodParams p) {
+    using L = TpcLayout<T>;
+    constexpr int S = L::kSlots;
+    constexpr int RE = L::kREntries;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float* bank_s = reinterpret_cast<float*>(smem_raw);                         // [128][8]
+    float2* warp_base = reinterpret_cast<float2*>(smem_raw + sizeof(float) * kIPhases * kITaps) +
+                        (size_t)(threadIdx.x >> 5) * L::kWarpFloat2;
+    float2* xs = warp_base;                    // [kXEntries][32]
+    float2* rs = warp_base + L::kXEntries * 32; // [RE][32]
+    const int lane = threadIdx.x & 31;
+
+    for (int i = threadIdx.x; i < kIPhases * kITaps; i += blockDim.x) { bank_s[i] = p.bank[i]; }
+
+    int ch = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool active = ch < p.n_channels;
+    if (!active) { ch = p.n_channels - 1; }     // compute a duplicate, store nothing
+    tdm_channel_state* __restrict__ sp = p.states + ch;
+
+    // ---- load carried state
+    float g = sp->agc_gain, fph = sp->fll_phase, ffr = sp->fll_freq;
+    SymbolState st;
+    st.mu = sp->tr_mu; st.om = sp->tr_omega; st.offset = sp->tr_offset;
+    st.cph = sp->costas_phase; st.cfr = sp->costas_freq; st.ph2 = sp->costas_ph2;
+    st.prev = sp->prev_sym; st.err_ptr = sp->err_ptr; st.err_disp = sp->err_disp;
+    st.err_partial = sp->err_partial; st.standarderr = sp->standarderr; st.sync = sp->sync;
+    st.nsym = 0;
+    float err_blocks[TDM_SYNC_BLOCKS];
+#pragma unroll
+    for (int j = 0; j < TDM_SYNC_BLOCKS; ++j) { err_blocks[j] = sp->err_blocks[j]; }
+    // delay line: linear index q (0..63 = carried history, 64+n = new sample n) lives in ring
+    // slot (1 + q/T) mod S, position q%T;  RRC ring: linear q' (0..6 history, 7+n new) at q' & (RE-1)
+    {
+        const float2* xh = reinterpret_cast<const float2*>(sp->x_hist);
+        for (int m = 0; m < kHist; ++m) { xs[((1 + m / T) * T + (m % T)) * 32 + lane] = xh[m]; }
+        const float2* rh = reinterpret_cast<const float2*>(sp->r_hist);
+        for (int j = 0; j < kITaps - 1; ++j) { rs[j * 32 + lane] = rh[j]; }
+    }
+    __syncthreads();   // bank_s visible
+
+    const float2* __restrict__ in = p.iq + (long long)ch * p.in_stride;
+    const long long out_base = (long long)ch * p.out_stride;
+    const int count = p.count;
+    const int nblk = (count + T - 1) / T;
+
+    float2 cur[T], nxt[T];
+#pragma unroll
+    for (int i = 0; i < T; ++i) { cur[i] = (i < count) ? __ldg(in + i) : make_float2(0.f, 0.f); }
+
+    int slot = 0;
+    for (int blk = 0; blk < nblk; ++blk) {
+        const int n0 = blk * T;
+        const int valid = min(T, count - n0);
+        // prefetch the next block's input while this one computes
+#pragma unroll
+        for (int i = 0; i < T; ++i) {
+            const int n = n0 + T + i;
+            nxt[i] = (n < count) ? __ldg(in + n) : make_float2(0.f, 0.f);
+        }
+
+        // ---- old part: history terms of all T outputs (independent of this block's feedback)
+        float acc[T][6];
+#pragma unroll
+        for (int i = 0; i < T; ++i) {
+#pragma unroll
+            for (int c = 0; c < 6; ++c) { acc[i][c] = 0.f; }
+        }
+#pragma unroll
+        for (int m = 0; m < kHist; ++m) {
+            int hs = slot + 1 + m / T;
+            if (hs >= S) { hs -= S; }
+            const float2 h = xs[(hs * T + (m % T)) * 32 + lane];
+#pragma unroll
+            for (int i = 0; i < T; ++i) {
+                const int k = m - i;        // tap index of history sample m in output i's window
+                if (k >= 0) {
+                    acc[i][0] = fma_rn(p.be_a[k], h.x, acc[i][0]);
+                    acc[i][1] = fma_rn(p.be_a[k], h.y, acc[i][1]);
+                    acc[i][2] = fma_rn(p.be_b[k], h.x, acc[i][2]);
+                    acc[i][3] = fma_rn(p.be_b[k], h.y, acc[i][3]);
+                    acc[i][4] = fma_rn(p.rrc[k], h.x, acc[i][4]);
+                    acc[i][5] = fma_rn(p.rrc[k], h.y, acc[i][5]);
+                }
+            }
+        }
+
+        // ---- serial part: the recurrences, plus the <= T newest terms of each chain
+        float2 xnew[T];
+#pragma unroll
+        for (int i = 0; i < T; ++i) {
+            xnew[i] = make_float2(0.f, 0.f);
+            if (i < valid) {
+                // FastAGC [A.3]
+                const float yr = mul_rn(cur[i].x, g), yi = mul_rn(cur[i].y, g);
+                const float amp = __fsqrt_rn(fma_rn(yr, yr, mul_rn(yi, yi)));
+                g = fma_rn(sub_rn(p.agc_set_point, amp), p.agc_rate, g);
+                if (g > p.agc_max_gain) { g = p.agc_max_gain; }
+                // FLL de-rotation, fll.cpp:137-138
+                float sn, cs;
+                sincos_canon(fph, sn, cs);
+                const float xr = fma_rn(yr, cs, mul_rn(yi, sn));
+                const float xi = fma_rn(yi, cs, -mul_rn(yr, sn));
+                xnew[i] = make_float2(xr, xi);
+                // newest terms: sample i is tap 64 + i - ip of output ip >= i
+#pragma unroll
+                for (int ip = i; ip < T; ++ip) {
+                    const int k = kHist + i - ip;
+                    acc[ip][0] = fma_rn(p.be_a[k], xr, acc[ip][0]);
+                    acc[ip][1] = fma_rn(p.be_a[k], xi, acc[ip][1]);
+                    acc[ip][2] = fma_rn(p.be_b[k], xr, acc[ip][2]);
+                    acc[ip][3] = fma_rn(p.be_b[k], xi, acc[ip][3]);
+                    acc[ip][4] = fma_rn(p.rrc[k], xr, acc[ip][4]);
+                    acc[ip][5] = fma_rn(p.rrc[k], xi, acc[ip][5]);
+                }
+                // band-edge error and loop update, fll.cpp:143-145
+                const float hbe = fast_amplitude(sub_rn(acc[i][0], acc[i][3]), add_rn(acc[i][1], acc[i][2]));
+                const float lbe = fast_amplitude(add_rn(acc[i][0], acc[i][3]), sub_rn(acc[i][1], acc[i][2]));
+                const float ferr = sub_rn(hbe, lbe);
+                ffr = clampf(fma_rn(p.fll_beta, ferr, ffr), p.fll_min_freq, p.fll_max_freq);
+                fph = wrap_pi(add_rn(fph, ffr));
+                // matched-filter output -> interpolator ring
+                rs[((kITaps - 1 + n0 + i) & (RE - 1)) * 32 + lane] = make_float2(acc[i][4], acc[i][5]);
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < T; ++i) { xs[(slot * T + i) * 32 + lane] = xnew[i]; }
+
+        // ---- symbols that became computable in this block (complex_fd.cpp:96 `while (offset < count)`)
+        while (st.offset < n0 + valid) { do_symbol<RE>(p, bank_s, rs, lane, st, err_blocks, active, out_base); }
+
+        slot = (slot + 1 == S) ? 0 : slot + 1;
+#pragma unroll
+        for (int i = 0; i < T; ++i) { cur[i] = nxt[i]; }
+    }
+
+    // ---- carry state out
+    if (active) {
+        sp->agc_gain = g; sp->fll_phase = fph; sp->fll_freq = ffr;
+        sp->tr_mu = st.mu; sp->tr_omega = st.om; sp->tr_offset = st.offset - count;   // complex_fd.cpp:145
+        sp->costas_phase = st.cph; sp->costas_freq = st.cfr; sp->costas_ph2 = st.ph2;
+        sp->prev_sym = st.prev; sp->err_ptr = st.err_ptr; sp->err_disp = st.err_disp;
+        sp->err_partial = st.err_partial; sp->standarderr = st.standarderr; sp->sync = st.sync;
+        sp->n_samples += (unsigned long long)count;
+        sp->n_symbols += (unsigned long long)st.nsym;
+#pragma unroll
+        for (int j = 0; j < TDM_SYNC_BLOCKS; ++j) { sp->err_blocks[j] = err_blocks[j]; }
+        float2* xh = reinterpret_cast<float2*>(sp->x_hist);
+        for (int m = 0; m < kHist; ++m) {
+            const long long q = (long long)count + m;
+            xh[m] = xs[(int)(((1 + q / T) % S) * T + (q % T)) * 32 + lane];
+        }
+        float2* rh = reinterpret_cast<float2*>(sp->r_hist);
+        for (int j = 0; j < kITaps - 1; ++j) { rh[j] = rs[((count + j) & (RE - 1)) * 32 + lane]; }
+        p.out_counts[ch] = st.nsym;
+    }
+}
+
+template <int T>
+int launch_tpc(const DemodParams& p, cudaStream_t stream, int warps_per_cta) {
+    using L = TpcLayout<T>;
+    const int threads = 32 * warps_per_cta;
+    const size_t smem = sizeof(float) * kIPhases * kITaps + L::kWarpBytes * warps_per_cta;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaFuncSetAttribute(demod_tpc_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        attr_set = true;
+    }
+    const int grid = (p.n_channels + threads - 1) / threads;
+    demod_tpc_kernel<T><<<grid, threads, smem, stream>>>(p);
+    return cudaGetLastError() == cudaSuccess ? 1 : -1;
+}
+
+// ---------------------------------------------------------------------------------------
+// dibit packing for the multi-GPU gather: 4 symbols per byte, first symbol in bits 7..6.
+// ---------------------------------------------------------------------------------------
+__global__ void pack_dibits_kernel(const uint8_t* __restrict__ dibits, long long in_stride,
+                                   const int* __restrict__ counts, uint8_t* __restrict__ packed,
+                                   long long out_stride, long long max_bytes) {
+    const int ch = blockIdx.y;
+    const int n = counts[ch];
+    const uint8_t* src = dibits + (long long)ch * in_stride;
+    uint8_t* dst = packed + (long long)ch * out_stride;
+    for (long long j = blockIdx.x * (long long)blockDim.x + threadIdx.x; j < max_bytes;
+         j += (long long)gridDim.x * blockDim.x) {
+        uint32_t v = 0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const long long s = 4 * j + k;
+            const uint32_t d = (s < n) ? (src[s] & 3u) : 0u;
+            v |= d << (6 - 2 * k);
+        }
+        dst[j] = (uint8_t)v;
+    }
+}
+
+}  // namespace
+
+const char* demod_variant_name(int variant) {
+    switch (variant) {
+        case 1: return "tpc4";
+        case 2: return "tpc8";
+        case 3: return "tpc4x4";
+        default: return "auto";
+    }
+}
+
+int launch_demod(const DemodParams& p, int variant, cudaStream_t stream) {
+    if (p.n_channels <= 0) { return 0; }
+    if (variant == 0) { variant = 1; }
+    switch (variant) {
+        case 1: return launch_tpc<4>(p, stream, 1);
+        case 2: return launch_tpc<8>(p, stream, 1);
+        case 3: return launch_tpc<4>(p, stream, 4);
+        default: return -1;
+    }
+}
+
+int launch_pack_dibits(const uint8_t* dibits, long long in_stride, const int* counts, uint8_t* packed,
+                       long long out_stride, int n_channels, long long max_syms, cudaStream_t stream) {
+    if (n_channels <= 0) { return 0; }
+    const long long max_bytes = (max_syms + 3) / 4;
+    if (max_bytes <= 0) { return 0; }
+    const int threads = 256;
+    long long gx = (max_bytes + threads - 1) / threads;
+    if (gx > 1024) { gx = 1024; }
+    dim3 grid((unsigned)gx, (unsigned)n_channels);
+    pack_dibits_kernel<<<grid, threads, 0, stream>>>(dibits, in_stride, counts, packed, out_stride, max_bytes);
+    return cudaGetLastError() == cudaSuccess ? 1 : -1;
+}
+
+}  // namespace tdm

@@ -1,0 +1,47 @@
+// tdm_kernels.cuh -- launch interface between the C-ABI layer (tdm_api.cu) and the
+// sm_100a kernels (tdm_kernels.cu, tdm_synth.cu).  Internal; the public surface is
+// include/tdm_b200.h.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "tdm_b200.h"
+
+namespace tdm {
+
+// Everything a demod launch needs, passed BY VALUE as a __grid_constant__ kernel
+// parameter: it then lives in the constant bank, so the FIR taps are immediate
+// constant-bank operands of the FFMAs (no loads, no registers), and two handles with
+// different configurations never share mutable __constant__ state.
+struct DemodParams {
+    // FIR taps, oldest sample first, zero-padded at the old end to TDM_MAX_TAPS.
+    float be_a[TDM_MAX_TAPS];   // band-edge pair: hbe taps = a + jb, lbe taps = a - jb
+    float be_b[TDM_MAX_TAPS];
+    float rrc[TDM_MAX_TAPS];
+    float agc_rate, agc_set_point, agc_max_gain;
+    float fll_beta, fll_min_freq, fll_max_freq;
+    float tr_alpha, tr_beta, tr_min_omega, tr_max_omega;
+    float costas_alpha, costas_beta, costas_min_freq, costas_max_freq;
+    const float* bank;              // device [128][8] interpolator polyphase bank
+    const float2* iq;               // [C][in_stride]
+    long long in_stride;
+    int count;                      // samples per channel this launch
+    int n_channels;
+    float2* syms;                   // [C][out_stride] or nullptr
+    uint8_t* dibits;                // [C][out_stride] or nullptr
+    uint8_t* bits;                  // [C][2*out_stride] or nullptr
+    long long out_stride;
+    int* out_counts;                // [C]
+    tdm_channel_state* states;      // [C]
+};
+
+// variant: 0 = auto.  Returns the number of kernels launched, or <0 on launch error.
+int launch_demod(const DemodParams& p, int variant, cudaStream_t stream);
+const char* demod_variant_name(int variant);
+
+int launch_pack_dibits(const uint8_t* dibits, long long in_stride, const int* counts, uint8_t* packed,
+                       long long out_stride, int n_channels, long long max_syms, cudaStream_t stream);
+
+int launch_synth(const tdm_synth_params& sp, int n_channels, long long n_samples, long long stride,
+                 int first_channel, float2* iq, uint8_t* tx_dibits, long long tx_stride, cudaStream_t stream);
+
+}  // namespace tdm
