@@ -14,7 +14,7 @@
  * Recipe for channel c, sample n (fs = 36 kS/s, 2 samples/symbol):
  *   a_k     = hash(seed_data+c, 16+k) & 3          absolute QPSK index of symbol k
  *   idx_k   = 2 a_k + (k & 1)                      phase of symbol k in units of pi/4
- *   dibit_k = map[(idx_k - idx_{k-1}) & 7]         1->00, 3->01, 5->11, 7->10   (idx_{-1} = 0)
+ *   dibit_k = map[(idx_k - idx_{k-1}) & 7]         1->00, 3->01, 5->11, 7->10   (idx_{-1} = 7)
  *   s[n]    = A e^{j(2 pi df n / fs + phi0)} sum_k e^{j pi idx_k / 4} h(n - 2k - 2 tau)  +  w[n]
  *   h       = root raised cosine, beta 0.35, Ts = 2 samples, support |t| <= 33
  *   df, tau, A, phi0 = draws 0..3 of hash(seed_data+c, .)
@@ -57,7 +57,7 @@ void sg_channel_draw(const sg_params* p, int c, sg_channel* out) {
 }
 
 static inline int sg_abs_index(uint64_t seed, int64_t k) {
-    if (k < 0) { return 0; }
+    if (k < 0) { return 7; } /* virtual symbol -1: keeps the first increment odd */
     return (int)(2 * (sg_hash(seed, 16 + (uint64_t)k) & 3) + (uint64_t)(k & 1));
 }
 

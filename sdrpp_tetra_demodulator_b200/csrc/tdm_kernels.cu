@@ -35,6 +35,7 @@ namespace {
 
 constexpr int kHist = TDM_HIST;            // 64
 constexpr int kTaps = TDM_MAX_TAPS;        // 65
+constexpr int kTapPad = TDM_TAP_PAD;
 constexpr int kITaps = TDM_INTERP_TAPS;    // 8
 constexpr int kIPhases = TDM_INTERP_PHASES;
 
@@ -160,8 +161,18 @@ __device__ __forceinline__ void do_symbol(const DemodParams& p, const float* __r
 }
 
 // ---------------------------------------------------------------------------------------
-// Variant tpc<T>: thread per channel, one warp per CTA (so consecutive warps land on
-// different SMs and each gets a whole SM's issue slots and shared-memory bandwidth).
+// Variant tpc<T>: thread per channel, time in blocks of T samples.
+//
+// Instruction-cache discipline: the first version of this kernel unrolled everything
+// (53 KB of SASS per block iteration) and ncu showed `stall_no_instruction` as the top
+// stall at IPC 0.36.  The hot loop is therefore kept ROLLED and small (about 10 KB):
+//   * old part: a loop over the 64/T history slots; each iteration loads T history
+//     samples and the 2T-1 taps per filter they meet (uniform constant-bank loads from
+//     the T-1-zero-padded tap tables, tpad[f][s*T + j-i+T-1]) and does T*T*6 FMAs;
+//   * serial part: a loop over the T samples; the T in-flight chains sit in a register
+//     shift-register, so position q always meets tap 64-q (an immediate constant-bank
+//     operand) and the loop body does not depend on the sample index;
+//   * symbol part: do_symbol(), called from a while loop.
 // ---------------------------------------------------------------------------------------
 template <int T>
 __global__ void __launch_bounds__(128) demod_tpc_kernel(const __grid_constant__ DemodParams p) {
@@ -172,7 +183,7 @@ __global__ void __launch_bounds__(128) demod_tpc_kernel(const __grid_constant__ 
     float* bank_s = reinterpret_cast<float*>(smem_raw);                         // [128][8]
     float2* warp_base = reinterpret_cast<float2*>(smem_raw + sizeof(float) * kIPhases * kITaps) +
                         (size_t)(threadIdx.x >> 5) * L::kWarpFloat2;
-    float2* xs = warp_base;                    // [kXEntries][32]
+    float2* xs = warp_base;                     // [kXEntries][32]
     float2* rs = warp_base + L::kXEntries * 32; // [RE][32]
     const int lane = threadIdx.x & 31;
 
@@ -214,6 +225,7 @@ __global__ void __launch_bounds__(128) demod_tpc_kernel(const __grid_constant__ 
     for (int i = 0; i < T; ++i) { cur[i] = (i < count) ? __ldg(in + i) : make_float2(0.f, 0.f); }
 
     int slot = 0;
+#pragma unroll 1
     for (int blk = 0; blk < nblk; ++blk) {
         const int n0 = blk * T;
         const int valid = min(T, count - n0);
@@ -224,72 +236,86 @@ __global__ void __launch_bounds__(128) demod_tpc_kernel(const __grid_constant__ 
             nxt[i] = (n < count) ? __ldg(in + n) : make_float2(0.f, 0.f);
         }
 
-        // ---- old part: history terms of all T outputs (independent of this block's feedback)
+        // ---- old part: history terms of all T outputs (independent of this block's feedback).
+        // acc[i][*] is the chain of output i; history sample m = s*T + j meets it at tap m - i, which
+        // is entry j - i + T - 1 of the padded table row starting at s*T (negative taps read zeros).
         float acc[T][6];
 #pragma unroll
         for (int i = 0; i < T; ++i) {
 #pragma unroll
             for (int c = 0; c < 6; ++c) { acc[i][c] = 0.f; }
         }
+        {
+            int hs = slot + 1;
+#pragma unroll 1
+            for (int s = 0; s < kHist / T; ++s) {
+                if (hs >= S) { hs -= S; }
+                float ta[2 * T - 1], tb[2 * T - 1], tr[2 * T - 1];
 #pragma unroll
-        for (int m = 0; m < kHist; ++m) {
-            int hs = slot + 1 + m / T;
-            if (hs >= S) { hs -= S; }
-            const float2 h = xs[(hs * T + (m % T)) * 32 + lane];
-#pragma unroll
-            for (int i = 0; i < T; ++i) {
-                const int k = m - i;        // tap index of history sample m in output i's window
-                if (k >= 0) {
-                    acc[i][0] = fma_rn(p.be_a[k], h.x, acc[i][0]);
-                    acc[i][1] = fma_rn(p.be_a[k], h.y, acc[i][1]);
-                    acc[i][2] = fma_rn(p.be_b[k], h.x, acc[i][2]);
-                    acc[i][3] = fma_rn(p.be_b[k], h.y, acc[i][3]);
-                    acc[i][4] = fma_rn(p.rrc[k], h.x, acc[i][4]);
-                    acc[i][5] = fma_rn(p.rrc[k], h.y, acc[i][5]);
+                for (int c = 0; c < 2 * T - 1; ++c) {
+                    ta[c] = p.tpad[0][s * T + c];
+                    tb[c] = p.tpad[1][s * T + c];
+                    tr[c] = p.tpad[2][s * T + c];
                 }
+#pragma unroll
+                for (int j = 0; j < T; ++j) {
+                    const float2 h = xs[(hs * T + j) * 32 + lane];
+#pragma unroll
+                    for (int i = 0; i < T; ++i) {
+                        const int c = j - i + T - 1;
+                        acc[i][0] = fma_rn(ta[c], h.x, acc[i][0]);
+                        acc[i][1] = fma_rn(ta[c], h.y, acc[i][1]);
+                        acc[i][2] = fma_rn(tb[c], h.x, acc[i][2]);
+                        acc[i][3] = fma_rn(tb[c], h.y, acc[i][3]);
+                        acc[i][4] = fma_rn(tr[c], h.x, acc[i][4]);
+                        acc[i][5] = fma_rn(tr[c], h.y, acc[i][5]);
+                    }
+                }
+                ++hs;
             }
         }
 
-        // ---- serial part: the recurrences, plus the <= T newest terms of each chain
-        float2 xnew[T];
+        // ---- serial part: the recurrences, plus the <= T newest terms of each chain.
+        // Shift-register form: before step i, acc[q] is the chain of output i+q; the new sample is
+        // tap 64-q of that output.  After the step the finished chain acc[0] is consumed and the
+        // register file shifts down by one (positions past T-1-i hold don't-care values).
+#pragma unroll 1
+        for (int i = 0; i < valid; ++i) {
+            // FastAGC [A.3]
+            const float yr = mul_rn(cur[0].x, g), yi = mul_rn(cur[0].y, g);
+            const float amp = __fsqrt_rn(fma_rn(yr, yr, mul_rn(yi, yi)));
+            g = fma_rn(sub_rn(p.agc_set_point, amp), p.agc_rate, g);
+            if (g > p.agc_max_gain) { g = p.agc_max_gain; }
+            // FLL de-rotation, fll.cpp:137-138
+            float sn, cs;
+            sincos_canon(fph, sn, cs);
+            const float xr = fma_rn(yr, cs, mul_rn(yi, sn));
+            const float xi = fma_rn(yi, cs, -mul_rn(yr, sn));
+            xs[(slot * T + i) * 32 + lane] = make_float2(xr, xi);
 #pragma unroll
-        for (int i = 0; i < T; ++i) {
-            xnew[i] = make_float2(0.f, 0.f);
-            if (i < valid) {
-                // FastAGC [A.3]
-                const float yr = mul_rn(cur[i].x, g), yi = mul_rn(cur[i].y, g);
-                const float amp = __fsqrt_rn(fma_rn(yr, yr, mul_rn(yi, yi)));
-                g = fma_rn(sub_rn(p.agc_set_point, amp), p.agc_rate, g);
-                if (g > p.agc_max_gain) { g = p.agc_max_gain; }
-                // FLL de-rotation, fll.cpp:137-138
-                float sn, cs;
-                sincos_canon(fph, sn, cs);
-                const float xr = fma_rn(yr, cs, mul_rn(yi, sn));
-                const float xi = fma_rn(yi, cs, -mul_rn(yr, sn));
-                xnew[i] = make_float2(xr, xi);
-                // newest terms: sample i is tap 64 + i - ip of output ip >= i
+            for (int q = 0; q < T; ++q) {
+                acc[q][0] = fma_rn(p.be_a[kHist - q], xr, acc[q][0]);
+                acc[q][1] = fma_rn(p.be_a[kHist - q], xi, acc[q][1]);
+                acc[q][2] = fma_rn(p.be_b[kHist - q], xr, acc[q][2]);
+                acc[q][3] = fma_rn(p.be_b[kHist - q], xi, acc[q][3]);
+                acc[q][4] = fma_rn(p.rrc[kHist - q], xr, acc[q][4]);
+                acc[q][5] = fma_rn(p.rrc[kHist - q], xi, acc[q][5]);
+            }
+            // band-edge error and loop update, fll.cpp:143-145
+            const float hbe = fast_amplitude(sub_rn(acc[0][0], acc[0][3]), add_rn(acc[0][1], acc[0][2]));
+            const float lbe = fast_amplitude(add_rn(acc[0][0], acc[0][3]), sub_rn(acc[0][1], acc[0][2]));
+            const float ferr = sub_rn(hbe, lbe);
+            ffr = clampf(fma_rn(p.fll_beta, ferr, ffr), p.fll_min_freq, p.fll_max_freq);
+            fph = wrap_pi(add_rn(fph, ffr));
+            // matched-filter output -> interpolator ring
+            rs[((kITaps - 1 + n0 + i) & (RE - 1)) * 32 + lane] = make_float2(acc[0][4], acc[0][5]);
 #pragma unroll
-                for (int ip = i; ip < T; ++ip) {
-                    const int k = kHist + i - ip;
-                    acc[ip][0] = fma_rn(p.be_a[k], xr, acc[ip][0]);
-                    acc[ip][1] = fma_rn(p.be_a[k], xi, acc[ip][1]);
-                    acc[ip][2] = fma_rn(p.be_b[k], xr, acc[ip][2]);
-                    acc[ip][3] = fma_rn(p.be_b[k], xi, acc[ip][3]);
-                    acc[ip][4] = fma_rn(p.rrc[k], xr, acc[ip][4]);
-                    acc[ip][5] = fma_rn(p.rrc[k], xi, acc[ip][5]);
-                }
-                // band-edge error and loop update, fll.cpp:143-145
-                const float hbe = fast_amplitude(sub_rn(acc[i][0], acc[i][3]), add_rn(acc[i][1], acc[i][2]));
-                const float lbe = fast_amplitude(add_rn(acc[i][0], acc[i][3]), sub_rn(acc[i][1], acc[i][2]));
-                const float ferr = sub_rn(hbe, lbe);
-                ffr = clampf(fma_rn(p.fll_beta, ferr, ffr), p.fll_min_freq, p.fll_max_freq);
-                fph = wrap_pi(add_rn(fph, ffr));
-                // matched-filter output -> interpolator ring
-                rs[((kITaps - 1 + n0 + i) & (RE - 1)) * 32 + lane] = make_float2(acc[i][4], acc[i][5]);
+            for (int q = 0; q < T - 1; ++q) {
+#pragma unroll
+                for (int c = 0; c < 6; ++c) { acc[q][c] = acc[q + 1][c]; }
+                cur[q] = cur[q + 1];
             }
         }
-#pragma unroll
-        for (int i = 0; i < T; ++i) { xs[(slot * T + i) * 32 + lane] = xnew[i]; }
 
         // ---- symbols that became computable in this block (complex_fd.cpp:96 `while (offset < count)`)
         while (st.offset < n0 + valid) { do_symbol<RE>(p, bank_s, rs, lane, st, err_blocks, active, out_base); }
@@ -322,15 +348,20 @@ __global__ void __launch_bounds__(128) demod_tpc_kernel(const __grid_constant__ 
 }
 
 template <int T>
-int launch_tpc(const DemodParams& p, cudaStream_t stream, int warps_per_cta) {
+int launch_tpc(const DemodParams& p_in, cudaStream_t stream, int warps_per_cta) {
     using L = TpcLayout<T>;
+    DemodParams p = p_in;
+    // tap tables padded with T-1 leading zeros (see the old-part loop)
+    const float* src[3] = { p.be_a, p.be_b, p.rrc };
+    for (int f = 0; f < 3; ++f) {
+        for (int j = 0; j < kTapPad; ++j) {
+            const int k = j - (T - 1);
+            p.tpad[f][j] = (k >= 0 && k < kTaps) ? src[f][k] : 0.f;
+        }
+    }
     const int threads = 32 * warps_per_cta;
     const size_t smem = sizeof(float) * kIPhases * kITaps + L::kWarpBytes * warps_per_cta;
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaFuncSetAttribute(demod_tpc_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-        attr_set = true;
-    }
+    cudaFuncSetAttribute(demod_tpc_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     const int grid = (p.n_channels + threads - 1) / threads;
     demod_tpc_kernel<T><<<grid, threads, smem, stream>>>(p);
     return cudaGetLastError() == cudaSuccess ? 1 : -1;

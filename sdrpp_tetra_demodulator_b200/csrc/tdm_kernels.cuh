@@ -6,6 +6,8 @@
 #include <stdint.h>
 #include "tdm_b200.h"
 
+#define TDM_TAP_PAD 88   /* >= 65 + 2*(T-1) for T <= 8, multiple of 4 */
+
 namespace tdm {
 
 // Everything a demod launch needs, passed BY VALUE as a __grid_constant__ kernel
@@ -17,6 +19,8 @@ struct DemodParams {
     float be_a[TDM_MAX_TAPS];   // band-edge pair: hbe taps = a + jb, lbe taps = a - jb
     float be_b[TDM_MAX_TAPS];
     float rrc[TDM_MAX_TAPS];
+    // the same three tables with T-1 leading zeros, filled per kernel variant at launch
+    float tpad[3][TDM_TAP_PAD];
     float agc_rate, agc_set_point, agc_max_gain;
     float fll_beta, fll_min_freq, fll_max_freq;
     float tr_alpha, tr_beta, tr_min_omega, tr_max_omega;

@@ -6,7 +6,7 @@
 //
 // Recipe (integer parts are exactly reproducible on any host, see tests/):
 //   a_k     = hash(seed_data+c, 16+k) & 3         idx_k = 2 a_k + (k & 1)     (units of pi/4)
-//   dibit_k = map[(idx_k - idx_{k-1}) & 7],  map: 1->00, 3->01, 5->11, 7->10,  idx_{-1} = 0
+//   dibit_k = map[(idx_k - idx_{k-1}) & 7],  map: 1->00, 3->01, 5->11, 7->10,  idx_{-1} = 7
 //   s[n]    = A e^{j(2 pi df n/fs + phi0)} sum_k e^{j pi idx_k/4} h(n - 2k - 2 tau) + w[n]
 //   h       = RRC beta 0.35, Ts = 2 samples, support |t| <= 33;  w = AWGN at Es/N0 = snr_db
 //   df, tau, A, phi0 = draws 0..3 of hash(seed_data+c, .);  noise from hash(seed_noise+c, n)
@@ -30,7 +30,7 @@ __host__ __device__ inline unsigned long long hash2(unsigned long long seed, uns
 }
 __host__ __device__ inline double u01(unsigned long long h) { return (double)(h >> 11) * (1.0 / 9007199254740992.0); }
 __host__ __device__ inline int abs_index(unsigned long long seed, long long k) {
-    if (k < 0) { return 0; }
+    if (k < 0) { return 7; } /* virtual symbol -1: keeps the first increment odd */
     return (int)(2 * (hash2(seed, 16 + (unsigned long long)k) & 3) + (unsigned long long)(k & 1));
 }
 

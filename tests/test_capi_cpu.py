@@ -1,0 +1,92 @@
+"""CPU tests of the boundary: the C-ABI library loads, exports every symbol include/tdm_b200.h declares,
+its host-only entry points work, and it refuses to run without a GPU (no CPU fallback)."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _header_functions():
+    src = open(os.path.join(ROOT, "include", "tdm_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(tdm_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol(pkg):
+    L = pkg.capi.lib()
+    declared = _header_functions()
+    assert len(declared) >= 20
+    for name in declared:
+        assert hasattr(L, name), f"{name} is declared in include/tdm_b200.h but not exported"
+    assert set(declared) == set(pkg.capi.EXPORTED_SYMBOLS)
+    assert L.tdm_abi_version() == 1
+
+
+def test_library_has_sm100a_code_only(pkg):
+    """the product is built for sm_100a (cuobjdump lists the embedded ELF architectures)"""
+    import shutil
+    import subprocess
+    if not shutil.which("cuobjdump"):
+        pytest.skip("cuobjdump not on PATH")
+    out = subprocess.run(["cuobjdump", "-lelf", pkg.capi.LIB_PATH], capture_output=True, text=True).stdout
+    archs = set(re.findall(r"sm_\d+a?", out))
+    assert archs == {"sm_100a"}, archs
+
+
+def test_library_does_not_link_the_oracle(pkg):
+    """the product path must not depend on anything under oracle/"""
+    import subprocess
+    out = subprocess.run(["ldd", pkg.capi.LIB_PATH], capture_output=True, text=True).stdout
+    assert "oracle" not in out and "tetra_ref" not in out
+    for root, _, files in os.walk(os.path.join(ROOT, "sdrpp_tetra_demodulator_b200")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h", ".hpp")):
+                text = open(os.path.join(root, f), errors="replace").read()
+                assert "import oracle" not in text and "from oracle" not in text and "oracle_b.h" not in text, f
+
+
+def test_create_without_gpu_fails_loudly(pkg):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    with pytest.raises(pkg.TdmError) as e:
+        pkg.Demodulator(4, 1024)
+    assert e.value.code == pkg.capi.TDM_ERR_NO_DEVICE
+    assert "no CPU fallback" in str(e.value)
+
+
+def test_argument_errors(pkg):
+    L = pkg.capi.lib()
+    h = C.c_void_p()
+    assert L.tdm_create(None, 0, 1024, 0, C.byref(h)) == pkg.capi.TDM_ERR_ARG
+    assert L.tdm_create(None, 4, 0, 0, C.byref(h)) == pkg.capi.TDM_ERR_ARG
+    assert L.tdm_create(None, 4, 1024, 0, None) == pkg.capi.TDM_ERR_ARG
+    cfg = pkg.default_config()
+    cfg.rrc_tap_count = 0
+    assert L.tdm_create(C.byref(cfg), 4, 1024, 0, C.byref(h)) == pkg.capi.TDM_ERR_UNSUPPORTED
+    assert L.tdm_process(None, None, 0, 0, None, None, None, 0, None, 0, 0) == pkg.capi.TDM_ERR_ARG
+    assert L.tdm_destroy(None) == pkg.capi.TDM_OK
+    assert b"null handle" in L.tdm_last_error()
+
+
+def test_short_filter_is_zero_padded_at_the_old_end(pkg):
+    cfg = pkg.default_config()
+    cfg.rrc_tap_count = 33
+    d = pkg.design_from_config(cfg)
+    rrc = np.array(d.rrc[:])
+    assert d.ntaps == 33 and np.all(rrc[:32] == 0) and np.all(rrc[32:] != 0)
+    assert np.all(np.array(d.be_a[:32]) == 0) and np.all(np.array(d.be_b[:32]) == 0)
+
+
+def test_channel_partition():
+    from sdrpp_tetra_demodulator_b200.sharding import channel_range
+    for C_, W in [(4096, 8), (4096, 1), (10, 4), (3, 8)]:
+        ranges = [channel_range(r, W, C_) for r in range(W)]
+        assert ranges[0][0] == 0 and ranges[-1][1] == C_
+        assert all(ranges[i][1] == ranges[i + 1][0] for i in range(W - 1))
+        sizes = [b - a for a, b in ranges]
+        assert max(sizes) - min(sizes) <= 1

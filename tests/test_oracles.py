@@ -1,0 +1,176 @@
+"""CPU tests: the two oracles against each other, against the golden fixtures made from the
+reference itself, and the host-side design code against the reference's own tap tables."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from conftest import golden_case, require_golden_input
+
+GOLDEN_CASES = ["small_c2_n4096", "batch_c8_n60000_snr30", "batch_c4_n60000_snr20", "cfg1_c1_n1e6_snr30"]
+
+
+def test_state_struct_sizes(O, pkg):
+    assert O.STATE_DTYPE.itemsize == 720 == pkg.capi.STATE_DTYPE.itemsize
+    assert C.sizeof(O.TdmDesign) == C.sizeof(pkg.TdmDesign)
+    assert C.sizeof(O.TdmConfig) == C.sizeof(pkg.TdmConfig) == 80
+
+
+def _design_arrays(d):
+    return (np.array(d.rrc[:], np.float32), np.array(d.be_a[:], np.float32), np.array(d.be_b[:], np.float32),
+            np.array(d.bank, np.float32).reshape(128, 8))
+
+
+def test_design_matches_reference_fixture(O, pkg):
+    """Product design code and Oracle B's independent restatement both reproduce, bit for bit, the tables
+    read out of the reference's own objects (tests/golden/design_default.npz, written by Oracle A)."""
+    import os
+    from conftest import GOLDEN
+    z = np.load(os.path.join(GOLDEN, "design_default.npz"))
+    for d in (pkg.design_from_config(pkg.default_config()), O.OracleB(1).design):
+        rrc, a, b, bank = _design_arrays(d)
+        assert np.array_equal(rrc, z["rrc"])
+        assert np.array_equal(a, z["hbe"][:, 0]) and np.array_equal(b, z["hbe"][:, 1])
+        # lower band-edge taps are the exact conjugate (src/dsp/fll.cpp:89-93)
+        assert np.array_equal(a, z["lbe"][:, 0]) and np.array_equal(-b, z["lbe"][:, 1])
+        assert np.array_equal(bank, z["bank"])
+        co = z["coeffs"]  # fll a,b,min,max | timing a,b,min,max | costas a,b,min,max | agc rate,set,max,init
+        got = np.array([0.0, d.fll_beta, d.fll_min_freq, d.fll_max_freq, d.tr_alpha, d.tr_beta, d.tr_min_omega,
+                        d.tr_max_omega, d.costas_alpha, d.costas_beta, d.costas_min_freq, d.costas_max_freq,
+                        d.agc_rate, d.agc_set_point, d.agc_max_gain, d.agc_init_gain], np.float32)
+        assert np.array_equal(got, co)
+
+
+def test_design_matches_live_reference(O, pkg):
+    if not O.have_ref():
+        pytest.skip("oracle/_ref not built here")
+    a = O.OracleA(1)
+    nt, rrc, lbe, hbe, bank, P, T = a.taps()
+    d = pkg.design_from_config(pkg.default_config())
+    r2, a2, b2, bank2 = _design_arrays(d)
+    assert (nt, P, T) == (65, 128, 8)
+    assert np.array_equal(r2, rrc) and np.array_equal(a2, hbe[:, 0]) and np.array_equal(b2, hbe[:, 1])
+    assert np.array_equal(bank2, bank)
+    assert abs(float(rrc.sum()) - 1.0001) < 2e-4 and abs(float(rrc[32]) - 0.547817) < 1e-5   # SURVEY.md A.6 probe
+
+
+def test_default_config_matches_plugin_constants(O, pkg):
+    """src/main.cpp:35-44,78-84"""
+    for cfg in (pkg.default_config(), O.OracleB.default_config()):
+        assert (cfg.symbolrate, cfg.samplerate, cfg.rrc_tap_count) == (18000.0, 36000.0, 65)
+        assert cfg.rrc_beta == float(np.float32(0.35)) and cfg.agc_rate == float(np.float32(0.02))
+        assert cfg.costas_bandwidth == float(np.float32(0.01)) and cfg.fll_bandwidth == float(np.float32(0.006))
+        assert abs(cfg.mu_gain - 0.017603) < 1e-6 and abs(cfg.omega_gain - 1.5636e-4) < 1e-8
+        assert cfg.omega_rel_limit == float(np.float32(0.02))
+
+
+def test_design_rejects_unsupported_tap_counts(pkg):
+    cfg = pkg.default_config()
+    cfg.rrc_tap_count = 66
+    with pytest.raises(pkg.TdmError) as e:
+        pkg.design_from_config(cfg)
+    assert e.value.code == pkg.capi.TDM_ERR_UNSUPPORTED
+
+
+def test_canonical_sincos_accuracy(O):
+    """the shared sin/cos must be a faithful stand-in for cosf/sinf: <= 2 ulp-ish absolute error on [-2pi, 2pi]"""
+    L = O.lib_b()
+    xs = np.linspace(-2 * np.pi, 2 * np.pi, 200001).astype(np.float32)
+    s, c = C.c_float(), C.c_float()
+    worst = 0.0
+    for x in xs[::7]:
+        L.ob_sincos(float(x), C.byref(s), C.byref(c))
+        worst = max(worst, abs(s.value - np.sin(np.float64(x))), abs(c.value - np.cos(np.float64(x))))
+    assert worst < 2.5e-7, worst
+
+
+@pytest.mark.parametrize("name", GOLDEN_CASES)
+def test_oracle_b_bits_equal_reference_golden(O, name):
+    """Decoded dibits of the canonical-order restatement == the reference's own chain (fixture from Oracle A)."""
+    g = golden_case(name)
+    require_golden_input(g)
+    b = O.OracleB(g.n_channels)
+    counts, syms, dibits, _ = b.process(g.iq, nthreads=4)
+    for c in range(g.n_channels):
+        g.assert_dibits_match(c, dibits[c], counts[c])
+        assert abs(b.states[c]["standarderr"] - g.ref_standarderr[c]) < 5e-3
+    if g.ref_syms is not None:
+        n = g.ref_syms.shape[1]
+        err = np.abs(syms[:, :n] - g.ref_syms).max()
+        assert err < 0.15   # float trajectories are NOT expected to match the reference's (chaotic at 1 ulp)
+
+
+@pytest.mark.parametrize("name", GOLDEN_CASES[:3])
+def test_live_reference_reproduces_golden(O, name):
+    """Where oracle/_ref exists, it must reproduce the committed fixture exactly (the fixture is its output)."""
+    if not O.have_ref():
+        pytest.skip("oracle/_ref not built here")
+    g = golden_case(name)
+    require_golden_input(g)
+    a = O.OracleA(g.n_channels)
+    counts, _, dibits, bits = a.process(g.iq, want_syms=False, want_bits=True)
+    assert np.array_equal(counts, g.counts)
+    for c in range(g.n_channels):
+        n = int(counts[c])
+        assert np.array_equal(dibits[c, :n], g.dibits[c])
+        # BitUnpacker, src/dsp/bit_unpacker.cpp:6-7
+        assert np.array_equal(bits[c, 0:2 * n:2], dibits[c, :n] >> 1) and np.array_equal(bits[c, 1:2 * n:2], dibits[c, :n] & 1)
+    a.close()
+
+
+@pytest.mark.parametrize("chunk", [32768, 4097, 7])
+def test_oracle_b_chunk_invariance(O, chunk):
+    """SURVEY.md [PROBE]: the reference is bit-identical for chunk sizes 1e6/32768/4097/7; so is the restatement."""
+    iq = O.generate(2, 50001)
+    one = O.OracleB(2)
+    c1, s1, d1, _ = one.process(iq)
+    many = O.OracleB(2)
+    outs, outd, tot = [], [], np.zeros(2, int)
+    for n0 in range(0, iq.shape[1], chunk):
+        c, s, d, _ = many.process(np.ascontiguousarray(iq[:, n0:n0 + chunk]))
+        outs.append([s[k, :c[k]] for k in range(2)])
+        outd.append([d[k, :c[k]] for k in range(2)])
+        tot += c
+    assert np.array_equal(tot, c1)
+    for k in range(2):
+        assert np.array_equal(np.concatenate([o[k] for o in outd]), d1[k, :c1[k]])
+        assert np.array_equal(np.concatenate([o[k] for o in outs]).view(np.uint32), s1[k, :c1[k]].view(np.uint32))
+    for f in O.EXACT_STATE_FIELDS + O.METRIC_STATE_FIELDS:
+        assert np.array_equal(one.states[f], many.states[f]), f
+
+
+def test_reference_chunk_invariance(O):
+    if not O.have_ref():
+        pytest.skip("oracle/_ref not built here")
+    iq = O.generate(1, 30011)
+    a1 = O.OracleA(1)
+    c1, _, d1, _ = a1.process(iq, want_syms=False)
+    a2 = O.OracleA(1)
+    ds = []
+    for n0 in range(0, iq.shape[1], 4097):
+        c, _, d, _ = a2.process(np.ascontiguousarray(iq[:, n0:n0 + 4097]), want_syms=False)
+        ds.append(d[0, :c[0]])
+    assert np.array_equal(np.concatenate(ds), d1[0, :c1[0]])
+
+
+def test_tx_rx_roundtrip(O):
+    """Self-consistency: decoded dibits == transmitted dibits after a fixed lag once locked."""
+    C_, N = 6, 80000
+    iq = O.generate(C_, N)
+    b = O.OracleB(C_)
+    counts, _, dibits, bits = b.process(iq, want_syms=False, want_bits=True, nthreads=4)
+    for c in range(C_):
+        n = int(counts[c])
+        tx = O.tx_dibits(c, n + 64)
+        errs = [np.count_nonzero(dibits[c, lag + 20000:n] != tx[20000:n - lag]) for lag in range(10, 30)]
+        assert min(errs) == 0, (c, min(errs))
+        assert np.array_equal(bits[c, 0:2 * n:2], dibits[c, :n] >> 1)
+    assert b.states["sync"].all()
+
+
+def test_generator_mapping_is_bits2phase(O):
+    """src/decoder/src/phy/tetra_burst.c:99-104: 00->+pi/4, 01->+3pi/4, 11->-3pi/4, 10->-pi/4, i.e. phase
+    increments of 1,3,5,7 eighth-turns; the generator's dibits must be uniform over the four values."""
+    d = O.tx_dibits(3, 40000)
+    hist = np.bincount(d, minlength=4) / len(d)
+    assert set(np.unique(d)) == {0, 1, 2, 3} and np.all(np.abs(hist - 0.25) < 0.02)
