@@ -148,8 +148,10 @@ int tdm_create(const tdm_config* cfg, int32_t n_channels, int32_t max_chunk, int
 /* ~PI4DQPSK (src/dsp/pi4dqpsk.cpp:5-9). */
 int tdm_destroy(tdm_handle* h);
 
-/* Enqueue subsequent work on `cuda_stream` (a cudaStream_t cast to void*; NULL =
- * the handle's own stream). */
+/* Enqueue subsequent work on `cuda_stream` (a cudaStream_t cast to void*).  NULL is
+ * the CUDA legacy default stream, exactly as in the runtime API; TDM_OWN_STREAM goes
+ * back to the private non-blocking stream every handle is created with. */
+#define TDM_OWN_STREAM ((void*)(intptr_t)-1)
 int tdm_set_stream(tdm_handle* h, void* cuda_stream);
 
 /* Symbols a call with `count` input samples can emit at most, per channel:

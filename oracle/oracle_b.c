@@ -342,6 +342,9 @@ static int64_t ob_process_chunk(const tdm_design* d, tdm_channel_state* s, ob_wo
         om = ob_clampf(fmaf(d->tr_beta, terr, om), d->tr_min_omega, d->tr_max_omega);
         mu = mu + fmaf(d->tr_alpha, terr, om);
         float delta = floorf(mu);
+        /* non-finite guard shared with the kernel (unreachable for finite input) */
+        if (!(delta >= 0.0f)) { delta = 1.0f; }
+        if (delta > 1048576.0f) { delta = 1048576.0f; }
         offset += (int)delta;
         mu -= delta;
 

@@ -183,7 +183,7 @@ int tdm_destroy(tdm_handle* h) {
 
 int tdm_set_stream(tdm_handle* h, void* cuda_stream) {
     if (!h) { return fail(TDM_ERR_ARG, "null handle"); }
-    h->stream = cuda_stream ? (cudaStream_t)cuda_stream : h->own_stream;
+    h->stream = (cuda_stream == TDM_OWN_STREAM) ? h->own_stream : (cudaStream_t)cuda_stream;
     return TDM_OK;
 }
 

@@ -107,7 +107,11 @@ __device__ __forceinline__ void do_symbol(const DemodParams& p, const float* __r
 #endif
     st.om = clampf(fma_rn(p.tr_beta, terr, st.om), p.tr_min_omega, p.tr_max_omega);
     st.mu = add_rn(st.mu, fma_rn(p.tr_alpha, terr, st.om));
-    const float delta = floorf(st.mu);
+    float delta = floorf(st.mu);
+    // Non-finite guard (unreachable for finite input: delta is 1..3 then).  The reference would spin or
+    // hit UB in `offset += delta` on NaN/Inf; a GPU must not, so the advance is forced into [1, 2^20].
+    if (!(delta >= 0.0f)) { delta = 1.0f; }
+    if (delta > 1048576.0f) { delta = 1048576.0f; }
     st.offset += (int)delta;
     st.mu = sub_rn(st.mu, delta);
 

@@ -74,7 +74,10 @@ class Demodulator:
 
     # -- configuration / control
     def set_stream(self, cuda_stream_ptr: int | None) -> None:
-        capi.check(self._lib.tdm_set_stream(self._h, C.c_void_p(cuda_stream_ptr or 0)), "tdm_set_stream")
+        """cuda_stream_ptr: a cudaStream_t as an int (0 = CUDA's legacy default stream); None = the handle's
+        own private stream (TDM_OWN_STREAM)."""
+        ptr = C.c_void_p(-1) if cuda_stream_ptr is None else C.c_void_p(int(cuda_stream_ptr))
+        capi.check(self._lib.tdm_set_stream(self._h, ptr), "tdm_set_stream")
 
     def use_torch_stream(self) -> None:
         torch = _torch()
@@ -160,6 +163,9 @@ class Demodulator:
         in_stride = iq.stride(0) // 2
         s = self.max_symbols(n)
         dev = iq.device
+        # device tensors belong to torch's stream-ordered allocator: enqueue on torch's current stream so
+        # the launch is ordered after the producers of `iq` and before any consumer of the outputs
+        self.set_stream(torch.cuda.current_stream(dev).cuda_stream)
         if out is None:
             out = DemodResult(
                 torch.empty(self.n_channels, dtype=torch.int32, device=dev),
