@@ -372,6 +372,274 @@ int launch_tpc(const DemodParams& p_in, cudaStream_t stream, int warps_per_cta) 
 }
 
 // ---------------------------------------------------------------------------------------
+// Variant ws<8>: warp-specialised software pipeline, 32 channels per CTA, 5 warps.
+//
+// The thread-per-channel kernel makes ONE warp carry all ~700 instructions per sample of
+// its 32 channels, and at 4096 channels only 128 of the GPU's 592 warp schedulers have a
+// warp at all.  Here the same arithmetic (same chains, same order) is cut by ROLE, so the
+// only warp that sits on the sample-rate recurrence executes ~165 instructions per sample
+// and four more schedulers per 32 channels do the rest concurrently:
+//
+//   warp 0  LOOP   AGC + FLL recurrence; adds the 2T-ish newest terms of the P/Q chains
+//   warp 1  P-far  the older 56-i terms of the two P chains (band-edge real-tap sums)
+//   warp 2  Q-far  same for the two Q chains
+//   warp 3  RRC    the complete matched-filter chains (not on the feedback path at all)
+//   warp 4  SYM    timing recovery, Costas, slicer, differential decoder
+//
+// Time advances in ticks of T = 8 samples with one __syncthreads() per tick; at tick t
+//   LOOP works on block t, P/Q-far prepare block t+1 (they need x only up to block t-1),
+//   RRC filters block t-1, SYM consumes the matched-filter outputs of block t-2.
+// All hand-offs go through shared-memory rings indexed by absolute sample position, so
+// the double buffering is implicit.  Chains still add terms in ascending tap order:
+// far part (P/Q warp) -> previous block's 8 samples -> own block (LOOP warp).
+// ---------------------------------------------------------------------------------------
+constexpr int kWsT = 8;
+constexpr int kWsXSlots = 16;                        // x ring: 16 blocks of 8 samples
+constexpr int kWsXEntries = kWsXSlots * kWsT;        // 128
+constexpr int kWsREntries = 32;                      // matched-filter output ring
+constexpr int kWsFar = kHist / kWsT - 1;             // 7 blocks of history feed the far part
+struct WsSmem {
+    float bank[kIPhases * kITaps];
+    float2 xs[kWsXEntries][32];
+    float2 rs[kWsREntries][32];
+    float2 pfar[2][kWsT][32];
+    float2 qfar[2][kWsT][32];
+};
+
+// two chains (re, im) of one real-tap filter for the T outputs of block b, over x-ring blocks
+// [first, first+nblocks) in linear-q block units; table row tp is padded with T-1 leading zeros
+template <int NB>
+__device__ __forceinline__ void ws_fir_blocks(const float* __restrict__ tp, const float2 (*xs)[32], int lane,
+                                              int qblock0, float (&acc)[kWsT][2]) {
+    constexpr int T = kWsT;
+#pragma unroll 1
+    for (int s = 0; s < NB; ++s) {
+        float tt[2 * T - 1];
+#pragma unroll
+        for (int c = 0; c < 2 * T - 1; ++c) { tt[c] = tp[s * T + c]; }
+        const int slot = (qblock0 + s) & (kWsXSlots - 1);
+#pragma unroll
+        for (int j = 0; j < T; ++j) {
+            const float2 h = xs[slot * T + j][lane];
+#pragma unroll
+            for (int i = 0; i < T; ++i) {
+                acc[i][0] = fma_rn(tt[j - i + T - 1], h.x, acc[i][0]);
+                acc[i][1] = fma_rn(tt[j - i + T - 1], h.y, acc[i][1]);
+            }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(160) demod_ws_kernel(const __grid_constant__ DemodParams p) {
+    constexpr int T = kWsT;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    WsSmem& sm = *reinterpret_cast<WsSmem*>(smem_raw);
+    const int lane = threadIdx.x & 31;
+    const int role = threadIdx.x >> 5;
+
+    for (int i = threadIdx.x; i < kIPhases * kITaps; i += blockDim.x) { sm.bank[i] = p.bank[i]; }
+
+    int ch = blockIdx.x * 32 + lane;
+    const bool active = ch < p.n_channels;
+    if (!active) { ch = p.n_channels - 1; }
+    tdm_channel_state* __restrict__ sp = p.states + ch;
+    const int count = p.count;
+    const int nblk = (count + T - 1) / T;
+
+    // rings: x linear index q (0..63 carried history, 64+n new sample n) -> slot (q/T) & 15, pos q%T;
+    //        matched-filter linear index q' (0..6 history, 7+n new) -> q' & 31
+    // Ring entries that are read before they are first written (the tail of a partial last block, met
+    // only by ZERO taps) must still be finite: 0 * NaN would poison a chain.  Clear everything past the
+    // carried history once.
+    for (int i = threadIdx.x; i < (kWsXEntries - kHist) * 32; i += blockDim.x) {
+        sm.xs[kHist + i / 32][i % 32] = make_float2(0.f, 0.f);
+    }
+    if (role == 1) {
+        const float2* xh = reinterpret_cast<const float2*>(sp->x_hist);
+        for (int m = 0; m < kHist; ++m) { sm.xs[m][lane] = xh[m]; }
+    }
+    if (role == 3) {
+        const float2* rh = reinterpret_cast<const float2*>(sp->r_hist);
+        for (int j = 0; j < kITaps - 1; ++j) { sm.rs[j][lane] = rh[j]; }
+    }
+
+    // ---- role-private state
+    float g = 0.f, fph = 0.f, ffr = 0.f;
+    float2 cur[T], nxt[T];
+    const float2* __restrict__ in = p.iq + (long long)ch * p.in_stride;
+    SymbolState st;
+    float err_blocks[TDM_SYNC_BLOCKS];
+    const long long out_base = (long long)ch * p.out_stride;
+    if (role == 0) {
+        g = sp->agc_gain; fph = sp->fll_phase; ffr = sp->fll_freq;
+#pragma unroll
+        for (int i = 0; i < T; ++i) { cur[i] = (i < count) ? __ldg(in + i) : make_float2(0.f, 0.f); }
+    }
+    if (role == 4) {
+        st.mu = sp->tr_mu; st.om = sp->tr_omega; st.offset = sp->tr_offset;
+        st.cph = sp->costas_phase; st.cfr = sp->costas_freq; st.ph2 = sp->costas_ph2;
+        st.prev = sp->prev_sym; st.err_ptr = sp->err_ptr; st.err_disp = sp->err_disp;
+        st.err_partial = sp->err_partial; st.standarderr = sp->standarderr; st.sync = sp->sync;
+        st.nsym = 0;
+#pragma unroll
+        for (int j = 0; j < TDM_SYNC_BLOCKS; ++j) { err_blocks[j] = sp->err_blocks[j]; }
+    }
+    __syncthreads();
+
+#pragma unroll 1
+    for (int t = -1; t <= nblk + 1; ++t) {
+        if (role == 0) {
+            // ================= LOOP: block b = t =================
+            if (t >= 0 && t < nblk) {
+                const int n0 = t * T;
+                const int valid = min(T, count - n0);
+#pragma unroll
+                for (int i = 0; i < T; ++i) {
+                    const int n = n0 + T + i;
+                    nxt[i] = (n < count) ? __ldg(in + n) : make_float2(0.f, 0.f);
+                }
+                // chains of this block's outputs: far part from the P/Q warps ...
+                float acc[T][4];
+#pragma unroll
+                for (int i = 0; i < T; ++i) {
+                    const float2 pf = sm.pfar[t & 1][i][lane], qf = sm.qfar[t & 1][i][lane];
+                    acc[i][0] = pf.x; acc[i][1] = pf.y; acc[i][2] = qf.x; acc[i][3] = qf.y;
+                }
+                // ... then the previous block's 8 samples (taps 56+j-i) ...
+                {
+                    const int slot = (t + 7) & (kWsXSlots - 1);      // q-block of sample block t-1
+#pragma unroll 2
+                    for (int j = 0; j < T; ++j) {
+                        const float2 h = sm.xs[slot * T + j][lane];
+                        float ta[T], tb[T];
+#pragma unroll
+                        for (int i = 0; i < T; ++i) {
+                            ta[i] = p.tpad[0][7 * T + j - i + T - 1];
+                            tb[i] = p.tpad[1][7 * T + j - i + T - 1];
+                        }
+#pragma unroll
+                        for (int i = 0; i < T; ++i) {
+                            acc[i][0] = fma_rn(ta[i], h.x, acc[i][0]);
+                            acc[i][1] = fma_rn(ta[i], h.y, acc[i][1]);
+                            acc[i][2] = fma_rn(tb[i], h.x, acc[i][2]);
+                            acc[i][3] = fma_rn(tb[i], h.y, acc[i][3]);
+                        }
+                    }
+                }
+                // ... then the block's own samples inside the recurrence (shift-register form)
+                const int xslot = (t + 8) & (kWsXSlots - 1);
+#pragma unroll 1
+                for (int i = 0; i < valid; ++i) {
+                    const float yr = mul_rn(cur[0].x, g), yi = mul_rn(cur[0].y, g);
+                    const float amp = __fsqrt_rn(fma_rn(yr, yr, mul_rn(yi, yi)));
+                    g = fma_rn(sub_rn(p.agc_set_point, amp), p.agc_rate, g);
+                    if (g > p.agc_max_gain) { g = p.agc_max_gain; }
+                    float sn, cs;
+                    sincos_canon(fph, sn, cs);
+                    const float xr = fma_rn(yr, cs, mul_rn(yi, sn));
+                    const float xi = fma_rn(yi, cs, -mul_rn(yr, sn));
+                    sm.xs[xslot * T + i][lane] = make_float2(xr, xi);
+#pragma unroll
+                    for (int q = 0; q < T; ++q) {
+                        acc[q][0] = fma_rn(p.be_a[kHist - q], xr, acc[q][0]);
+                        acc[q][1] = fma_rn(p.be_a[kHist - q], xi, acc[q][1]);
+                        acc[q][2] = fma_rn(p.be_b[kHist - q], xr, acc[q][2]);
+                        acc[q][3] = fma_rn(p.be_b[kHist - q], xi, acc[q][3]);
+                    }
+                    const float hbe = fast_amplitude(sub_rn(acc[0][0], acc[0][3]), add_rn(acc[0][1], acc[0][2]));
+                    const float lbe = fast_amplitude(add_rn(acc[0][0], acc[0][3]), sub_rn(acc[0][1], acc[0][2]));
+                    const float ferr = sub_rn(hbe, lbe);
+                    ffr = clampf(fma_rn(p.fll_beta, ferr, ffr), p.fll_min_freq, p.fll_max_freq);
+                    fph = wrap_pi(add_rn(fph, ffr));
+#pragma unroll
+                    for (int q = 0; q < T - 1; ++q) {
+#pragma unroll
+                        for (int c = 0; c < 4; ++c) { acc[q][c] = acc[q + 1][c]; }
+                        cur[q] = cur[q + 1];
+                    }
+                }
+#pragma unroll
+                for (int i = 0; i < T; ++i) { cur[i] = nxt[i]; }
+            }
+        } else if (role == 1 || role == 2) {
+            // ================= P-far / Q-far: block b = t + 1 =================
+            const int b = t + 1;
+            if (b < nblk) {
+                float acc[T][2];
+#pragma unroll
+                for (int i = 0; i < T; ++i) { acc[i][0] = 0.f; acc[i][1] = 0.f; }
+                ws_fir_blocks<kWsFar>(p.tpad[role - 1], sm.xs, lane, b, acc);
+                float2 (*dst)[32] = (role == 1) ? sm.pfar[b & 1] : sm.qfar[b & 1];
+#pragma unroll
+                for (int i = 0; i < T; ++i) { dst[i][lane] = make_float2(acc[i][0], acc[i][1]); }
+            }
+        } else if (role == 3) {
+            // ================= RRC: block b = t - 1 (all 65 taps; 9 ring blocks) =================
+            const int b = t - 1;
+            if (b >= 0 && b < nblk) {
+                float acc[T][2];
+#pragma unroll
+                for (int i = 0; i < T; ++i) { acc[i][0] = 0.f; acc[i][1] = 0.f; }
+                ws_fir_blocks<kWsFar + 2>(p.tpad[2], sm.xs, lane, b, acc);
+#pragma unroll
+                for (int i = 0; i < T; ++i) {
+                    sm.rs[(kITaps - 1 + b * T + i) & (kWsREntries - 1)][lane] = make_float2(acc[i][0], acc[i][1]);
+                }
+            }
+        } else {
+            // ================= SYM: symbols whose last input sample lies in block t - 2 =================
+            if (t >= 2) {
+                const int lim = min(count, (t - 1) * T);
+                while (st.offset < lim) {
+                    do_symbol<kWsREntries>(p, sm.bank, &sm.rs[0][0], lane, st, err_blocks, active, out_base);
+                }
+            }
+        }
+        __syncthreads();
+    }
+
+    // ---- carry state out
+    if (!active) { return; }
+    if (role == 0) {
+        sp->agc_gain = g; sp->fll_phase = fph; sp->fll_freq = ffr;
+        sp->n_samples += (unsigned long long)count;
+    } else if (role == 1) {
+        float2* xh = reinterpret_cast<float2*>(sp->x_hist);
+        for (int m = 0; m < kHist; ++m) {
+            const long long q = (long long)count + m;
+            xh[m] = sm.xs[(int)((q / T) & (kWsXSlots - 1)) * T + (int)(q % T)][lane];
+        }
+    } else if (role == 3) {
+        float2* rh = reinterpret_cast<float2*>(sp->r_hist);
+        for (int j = 0; j < kITaps - 1; ++j) { rh[j] = sm.rs[(count + j) & (kWsREntries - 1)][lane]; }
+    } else if (role == 4) {
+        sp->tr_mu = st.mu; sp->tr_omega = st.om; sp->tr_offset = st.offset - count;
+        sp->costas_phase = st.cph; sp->costas_freq = st.cfr; sp->costas_ph2 = st.ph2;
+        sp->prev_sym = st.prev; sp->err_ptr = st.err_ptr; sp->err_disp = st.err_disp;
+        sp->err_partial = st.err_partial; sp->standarderr = st.standarderr; sp->sync = st.sync;
+        sp->n_symbols += (unsigned long long)st.nsym;
+#pragma unroll
+        for (int j = 0; j < TDM_SYNC_BLOCKS; ++j) { sp->err_blocks[j] = err_blocks[j]; }
+        p.out_counts[ch] = st.nsym;
+    }
+}
+
+int launch_ws(const DemodParams& p_in, cudaStream_t stream) {
+    DemodParams p = p_in;
+    const float* src[3] = { p.be_a, p.be_b, p.rrc };
+    for (int f = 0; f < 3; ++f) {
+        for (int j = 0; j < kTapPad; ++j) {
+            const int k = j - (kWsT - 1);
+            p.tpad[f][j] = (k >= 0 && k < kTaps) ? src[f][k] : 0.f;
+        }
+    }
+    cudaFuncSetAttribute(demod_ws_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(WsSmem));
+    const int grid = (p.n_channels + 31) / 32;
+    demod_ws_kernel<<<grid, 160, sizeof(WsSmem), stream>>>(p);
+    return cudaGetLastError() == cudaSuccess ? 1 : -1;
+}
+
+// ---------------------------------------------------------------------------------------
 // dibit packing for the multi-GPU gather: 4 symbols per byte, first symbol in bits 7..6.
 // ---------------------------------------------------------------------------------------
 __global__ void pack_dibits_kernel(const uint8_t* __restrict__ dibits, long long in_stride,
@@ -401,6 +669,7 @@ const char* demod_variant_name(int variant) {
         case 1: return "tpc4";
         case 2: return "tpc8";
         case 3: return "tpc4x4";
+        case 4: return "ws8";
         default: return "auto";
     }
 }
@@ -412,6 +681,7 @@ int launch_demod(const DemodParams& p, int variant, cudaStream_t stream) {
         case 1: return launch_tpc<4>(p, stream, 1);
         case 2: return launch_tpc<8>(p, stream, 1);
         case 3: return launch_tpc<4>(p, stream, 4);
+        case 4: return launch_ws(p, stream);
         default: return -1;
     }
 }

@@ -17,7 +17,7 @@ from conftest import golden_case, require_golden_input
 
 pytestmark = pytest.mark.gpu
 
-VARIANTS = [1, 2, 3]
+VARIANTS = [1, 2, 3, 4]
 
 
 @pytest.fixture(scope="module")
@@ -114,8 +114,9 @@ def test_live_reference_when_present(O, pkg, torch_cuda):
     a.close()
 
 
+@pytest.mark.parametrize("variant", [0, 4])
 @pytest.mark.parametrize("chunk", [32768, 4097, 7])
-def test_chunk_invariance_and_streaming_state(O, pkg, torch_cuda, chunk):
+def test_chunk_invariance_and_streaming_state(O, pkg, torch_cuda, chunk, variant):
     """BASELINE.json configs[4] in miniature: state carried across launches; any chunking gives the
     single-shot result bit for bit (the reference is chunk invariant, SURVEY.md [PROBE])."""
     torch = torch_cuda
@@ -123,6 +124,7 @@ def test_chunk_invariance_and_streaming_state(O, pkg, torch_cuda, chunk):
     iq = O.generate(C_, N)
     dev = torch.from_numpy(iq).cuda()
     with pkg.Demodulator(C_, N) as one, pkg.Demodulator(C_, chunk) as many:
+        many.set_kernel_variant(variant)
         r1 = one.process(dev, symbols=True, dibits=True)
         torch.cuda.synchronize()
         c1, s1, d1 = r1.counts.cpu().numpy(), r1.symbols.cpu().numpy(), r1.dibits.cpu().numpy()
