@@ -486,8 +486,15 @@ __global__ void __launch_bounds__(160) demod_ws_kernel(const __grid_constant__ D
     }
     __syncthreads();
 
+#ifdef TDM_ROLE_TIMING
+    long long work_cycles = 0;
+    const long long t_begin = clock64();
+#endif
 #pragma unroll 1
     for (int t = -1; t <= nblk + 1; ++t) {
+#ifdef TDM_ROLE_TIMING
+        const long long c0 = clock64();
+#endif
         if (role == 0) {
             // ================= LOOP: block b = t =================
             if (t >= 0 && t < nblk) {
@@ -595,8 +602,17 @@ __global__ void __launch_bounds__(160) demod_ws_kernel(const __grid_constant__ D
                 }
             }
         }
+#ifdef TDM_ROLE_TIMING
+        work_cycles += clock64() - c0;
+#endif
         __syncthreads();
     }
+#ifdef TDM_ROLE_TIMING
+    if (blockIdx.x == 3 && lane == 0) {
+        printf("role %d: work %lld of %lld cycles (%.1f%%), per tick %lld\n", role, work_cycles, clock64() - t_begin,
+               100.0 * work_cycles / (double)(clock64() - t_begin), work_cycles / (nblk + 3));
+    }
+#endif
 
     // ---- carry state out
     if (!active) { return; }
