@@ -36,6 +36,17 @@
 
 #include <math.h>
 #include <pthread.h>
+#if defined(__x86_64__) || defined(__i386__)
+#include <xmmintrin.h>
+/* The canonical order is IEEE-754 with gradual underflow.  Any shared object built with -ffast-math that the
+ * host process happens to load (crtfastmath.o) switches the thread to flush-to-zero / denormals-are-zero, and
+ * new threads inherit that: force it off for the duration of a call, restore afterwards. */
+#define OB_FP_ENV_ENTER() unsigned ob_saved_csr = _mm_getcsr(); _mm_setcsr(ob_saved_csr & ~0x8040u)
+#define OB_FP_ENV_LEAVE() _mm_setcsr(ob_saved_csr)
+#else
+#define OB_FP_ENV_ENTER() (void)0
+#define OB_FP_ENV_LEAVE() (void)0
+#endif
 #include <stdlib.h>
 #include <string.h>
 
@@ -410,6 +421,7 @@ static int64_t ob_process_chunk(const tdm_design* d, tdm_channel_state* s, ob_wo
 
 int64_t ob_process(const tdm_design* d, tdm_channel_state* s, const float* iq, int64_t count,
                    float* syms, uint8_t* dibits, uint8_t* bits) {
+    OB_FP_ENV_ENTER();
     ob_work* w = (ob_work*)malloc(sizeof(ob_work));
     int64_t done = 0, nsym = 0;
     while (done < count) {
@@ -420,6 +432,7 @@ int64_t ob_process(const tdm_design* d, tdm_channel_state* s, const float* iq, i
         done += n;
     }
     free(w);
+    OB_FP_ENV_LEAVE();
     return nsym;
 }
 

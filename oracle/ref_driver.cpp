@@ -28,6 +28,17 @@
 #include <thread>
 #include <type_traits>
 #include <vector>
+#if defined(__x86_64__) || defined(__i386__)
+#include <xmmintrin.h>
+// IEEE gradual underflow regardless of what -ffast-math libraries the host process loaded (see oracle_b.c).
+struct FpEnvGuard {
+    unsigned saved;
+    FpEnvGuard() : saved(_mm_getcsr()) { _mm_setcsr(saved & ~0x8040u); }
+    ~FpEnvGuard() { _mm_setcsr(saved); }
+};
+#else
+struct FpEnvGuard {};
+#endif
 
 // Let the driver read protected loop state / tap tables for diagnostics and
 // for pinning Oracle B's tap design.  Standard headers are included above so
@@ -115,6 +126,7 @@ void tref_reset(void* h) {
 // bits (1/byte, 2 per dibit) may each be NULL.  Returns the symbol count.
 // Feeds the chain in calls of at most STREAM_BUFFER_SIZE samples, like SDR++.
 int64_t tref_process(void* h, int64_t count, const float* iq, float* syms, uint8_t* dibits, uint8_t* bits) {
+    FpEnvGuard fpenv;
     tref_chain* c = (tref_chain*)h;
     int64_t done = 0, nsym = 0;
     while (done < count) {

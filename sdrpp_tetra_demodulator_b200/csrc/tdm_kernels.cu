@@ -60,33 +60,44 @@ struct SymbolState {
     int nsym;
 };
 
-// One output symbol: interpolate at `offset`, timing-error update, Costas, slice, decode.
-// complex_fd.cpp:96-143, pi4dqpsk_costas.cpp:5-28, dqpsk_sym_extr.cpp:4-55, bit_unpacker.cpp:6-7.
+// Loop gains/limits of the symbol-rate loops, pinned in registers by the role that runs do_symbol().
+struct SymConsts {
+    float tr_alpha, tr_beta, tr_min, tr_max;
+    float c_alpha, c_beta, c_min, c_max;
+};
+__device__ __forceinline__ SymConsts load_sym_consts(const DemodParams& p) {
+    SymConsts k;
+    k.tr_alpha = pin(p.tr_alpha); k.tr_beta = pin(p.tr_beta); k.tr_min = pin(p.tr_min_omega); k.tr_max = pin(p.tr_max_omega);
+    k.c_alpha = pin(p.costas_alpha); k.c_beta = pin(p.costas_beta); k.c_min = pin(p.costas_min_freq); k.c_max = pin(p.costas_max_freq);
+    return k;
+}
+
+// Timing recovery for one output symbol (complex_fd.cpp:96-143): interpolate the matched-filter output at
+// `offset` with polyphase row floor(mu*128), derivative from the neighbouring rows, sign-decision-directed
+// error, PI update of (omega, mu), integer advance of `offset`.  Returns the interpolated symbol.
 template <int RE>
-__device__ __forceinline__ void do_symbol(const DemodParams& p, const float* __restrict__ bank_s,
-                                          const float2* __restrict__ rs, int lane, SymbolState& st,
-                                          float* __restrict__ err_blocks, bool active, long long out_base) {
-    // --- polyphase interpolation + derivative
+__device__ __forceinline__ float2 timing_step(const SymConsts& kc, const float* __restrict__ bank_s,
+                                              const float2* rs, int lane, float& mu, float& om, int& offset) {
     // phase = clamp(floor(mu*128), 0, 127) (complex_fd.cpp:101).  The clamp is done on the float and the
     // edge cases below are folded into one expression on purpose: with an integer min/max clamp followed
     // by `if (ph == 0) .. else if (ph == 127) ..`, ptxas 12.9 for sm_100a derived the `ph == 127` test from
     // the predicate output of VIMNMX.RELU and took the last-phase branch for ph == 0 (seen on hardware).
-    const float phf = fminf(fmaxf(floorf(mul_rn(st.mu, (float)kIPhases)), 0.0f), (float)(kIPhases - 1));
+    const float phf = fminf(fmaxf(floorf(mul_rn(mu, (float)kIPhases)), 0.0f), (float)(kIPhases - 1));
     const int ph = (int)phf;
     const int plo = max(ph - 1, 0);
     const int phi = min(ph + 1, kIPhases - 1);
     const float4* r0 = reinterpret_cast<const float4*>(bank_s + ph * kITaps);
     const float4* r1 = reinterpret_cast<const float4*>(bank_s + phi * kITaps);
     const float4* r2 = reinterpret_cast<const float4*>(bank_s + plo * kITaps);
-    float t0[8], t1[8], t2[8];
-    *reinterpret_cast<float4*>(&t0[0]) = r0[0]; *reinterpret_cast<float4*>(&t0[4]) = r0[1];
-    *reinterpret_cast<float4*>(&t1[0]) = r1[0]; *reinterpret_cast<float4*>(&t1[4]) = r1[1];
-    *reinterpret_cast<float4*>(&t2[0]) = r2[0]; *reinterpret_cast<float4*>(&t2[4]) = r2[1];
+    const float4 t0a = r0[0], t0b = r0[1], t1a = r1[0], t1b = r1[1], t2a = r2[0], t2b = r2[1];
+    const float t0[8] = { t0a.x, t0a.y, t0a.z, t0a.w, t0b.x, t0b.y, t0b.z, t0b.w };
+    const float t1[8] = { t1a.x, t1a.y, t1a.z, t1a.w, t1b.x, t1b.y, t1b.z, t1b.w };
+    const float t2[8] = { t2a.x, t2a.y, t2a.z, t2a.w, t2b.x, t2b.y, t2b.z, t2b.w };
     float yre = 0.f, yim = 0.f, are = 0.f, aim = 0.f, bre = 0.f, bim = 0.f;
 #pragma unroll
     for (int k = 0; k < kITaps; ++k) {
         // RRC outputs offset-7 .. offset live at linear ring index offset+k (7 history entries first)
-        const float2 v = rs[((st.offset + k) & (RE - 1)) * 32 + lane];
+        const float2 v = rs[((offset + k) & (RE - 1)) * 32 + lane];
         yre = fma_rn(t0[k], v.x, yre); yim = fma_rn(t0[k], v.y, yim);
         are = fma_rn(t1[k], v.x, are); aim = fma_rn(t1[k], v.y, aim);
         bre = fma_rn(t2[k], v.x, bre); bim = fma_rn(t2[k], v.y, bim);
@@ -99,44 +110,42 @@ __device__ __forceinline__ void do_symbol(const DemodParams& p, const float* __r
     const float dim = mul_rn(sub_rn(aim, bim), dscale);
     float terr = add_rn(yre > 0.f ? dre : -dre, yim > 0.f ? dim : -dim);
     terr = clampf(terr, -1.0f, 1.0f);
-#ifdef TDM_DEBUG_TRACE
-    if (out_base == 0 && st.nsym >= 10 && st.nsym < 22) {
-        printf("sym %d off %d ph %d y=(%g,%g) a=(%g,%g) b=(%g,%g) d=(%g,%g) terr=%g om=%g mu=%g alpha=%g beta=%g t0=%g,%g t1=%g,%g\n", st.nsym, st.offset, ph,
-               yre, yim, are, aim, bre, bim, dre, dim, terr, st.om, st.mu, p.tr_alpha, p.tr_beta, t0[3], t0[4], t1[3], t1[4]);
-    }
-#endif
-    st.om = clampf(fma_rn(p.tr_beta, terr, st.om), p.tr_min_omega, p.tr_max_omega);
-    st.mu = add_rn(st.mu, fma_rn(p.tr_alpha, terr, st.om));
-    float delta = floorf(st.mu);
+    om = clampf(fma_rn(kc.tr_beta, terr, om), kc.tr_min, kc.tr_max);
+    mu = add_rn(mu, fma_rn(kc.tr_alpha, terr, om));
+    float delta = floorf(mu);
     // Non-finite guard (unreachable for finite input: delta is 1..3 then).  The reference would spin or
     // hit UB in `offset += delta` on NaN/Inf; a GPU must not, so the advance is forced into [1, 2^20].
-    if (!(delta >= 0.0f)) { delta = 1.0f; }
-    if (delta > 1048576.0f) { delta = 1048576.0f; }
-    st.offset += (int)delta;
-    st.mu = sub_rn(st.mu, delta);
+    delta = (delta >= 0.0f) ? delta : 1.0f;
+    delta = fminf(delta, 1048576.0f);
+    offset += (int)delta;
+    mu = sub_rn(mu, delta);
+    return make_float2(yre, yim);
+}
 
-    // --- pi/4 Costas
+// pi/4 Costas loop, slicer, lock metric, differential decoder, bit unpack for one symbol
+// (pi4dqpsk_costas.cpp:5-28, dqpsk_sym_extr.cpp:4-55, bit_unpacker.cpp:6-7).
+__device__ __forceinline__ void costas_step(const DemodParams& p, const SymConsts& kc, float2 y, SymbolState& st,
+                                            float* __restrict__ err_blocks, bool active, long long out_base) {
     float sn, cs;
     sincos_canon(st.cph, sn, cs);
-    const float zr = fma_rn(yre, cs, mul_rn(yim, sn));
-    const float zi = fma_rn(yim, cs, -mul_rn(yre, sn));
+    const float zr = fma_rn(y.x, cs, mul_rn(y.y, sn));
+    const float zi = fma_rn(y.y, cs, -mul_rn(y.x, sn));
     const float two_pi_c = 2 * TDM_FL_M_PI;
-    st.ph2 = add_rn(st.ph2, -(TDM_FL_M_PI / 4.0f));
-    if (st.ph2 >= two_pi_c) { st.ph2 = sub_rn(st.ph2, two_pi_c); }
-    else if (st.ph2 <= -two_pi_c) { st.ph2 = add_rn(st.ph2, two_pi_c); }
+    float ph2 = add_rn(st.ph2, -(TDM_FL_M_PI / 4.0f));
+    ph2 = (ph2 >= two_pi_c) ? sub_rn(ph2, two_pi_c) : ((ph2 <= -two_pi_c) ? add_rn(ph2, two_pi_c) : ph2);
+    st.ph2 = ph2;
     float s2, c2;
-    sincos_canon(st.ph2, s2, c2);
+    sincos_canon(ph2, s2, c2);
     const float ur = fma_rn(zr, c2, -mul_rn(zi, s2));
     const float ui = fma_rn(zi, c2, mul_rn(zr, s2));
     float cerr = sub_rn(ur > 0.f ? ui : -ui, ui > 0.f ? ur : -ur);
     cerr = clampf(cerr, -1.0f, 1.0f);
-    st.cfr = clampf(fma_rn(p.costas_beta, cerr, st.cfr), p.costas_min_freq, p.costas_max_freq);
-    st.cph = wrap_pi(add_rn(st.cph, fma_rn(p.costas_alpha, cerr, st.cfr)));
+    st.cfr = clampf(fma_rn(kc.c_beta, cerr, st.cfr), kc.c_min, kc.c_max);
+    st.cph = wrap_pi(add_rn(st.cph, fma_rn(kc.c_alpha, cerr, st.cfr)));
 
     // --- slicer, sync metric, differential decode
     const bool a = ui < 0.f, b = ur < 0.f;
-    const float ideal = a ? (b ? -2.35619449f : -0.785398185f) : (b ? 2.35619449f : 0.785398185f);
-    const float dist = fabsf(sub_rn(ideal, atan2f(ui, ur)));
+    const float dist = quadrant_phase_error(ur, ui);     // |ideal.phase() - sym.phase()|, dqpsk_sym_extr.cpp:8-11
     st.err_partial = add_rn(st.err_partial, dist);
     st.err_ptr++;
     st.err_disp++;
@@ -162,6 +171,46 @@ __device__ __forceinline__ void do_symbol(const DemodParams& p, const float* __r
         if (p.bits) { reinterpret_cast<uchar2*>(p.bits)[o] = make_uchar2((uint8_t)((db >> 1) & 1u), (uint8_t)(db & 1u)); }
     }
     st.nsym++;
+}
+
+// One output symbol, both halves in the same thread (thread-per-channel variants).
+template <int RE>
+__device__ __forceinline__ void do_symbol(const DemodParams& p, const SymConsts& kc, const float* __restrict__ bank_s,
+                                          const float2* __restrict__ rs, int lane, SymbolState& st,
+                                          float* __restrict__ err_blocks, bool active, long long out_base) {
+    const float2 y = timing_step<RE>(kc, bank_s, rs, lane, st.mu, st.om, st.offset);
+    costas_step(p, kc, y, st, err_blocks, active, out_base);
+}
+
+// Constants of the sample-rate recurrences (AGC, FLL), pinned in registers for the serial loop.
+struct LoopConsts {
+    float agc_rate, agc_set, agc_max, fll_beta, fll_min, fll_max;
+};
+__device__ __forceinline__ LoopConsts load_loop_consts(const DemodParams& p) {
+    LoopConsts k;
+    k.agc_rate = pin(p.agc_rate); k.agc_set = pin(p.agc_set_point); k.agc_max = pin(p.agc_max_gain);
+    k.fll_beta = pin(p.fll_beta); k.fll_min = pin(p.fll_min_freq); k.fll_max = pin(p.fll_max_freq);
+    return k;
+}
+
+// AGC + de-rotation of one input sample (FastAGC [A.3]; fll.cpp:137-138).  Branch free.
+__device__ __forceinline__ float2 agc_derotate(const LoopConsts& lc, float2 in, float& g, float fph) {
+    const float yr = mul_rn(in.x, g), yi = mul_rn(in.y, g);
+    const float amp = sqrt_rn_nobranch(fma_rn(yr, yr, mul_rn(yi, yi)));
+    g = fma_rn(sub_rn(lc.agc_set, amp), lc.agc_rate, g);
+    g = g > lc.agc_max ? lc.agc_max : g;
+    float sn, cs;
+    sincos_canon(fph, sn, cs);
+    return make_float2(fma_rn(yr, cs, mul_rn(yi, sn)), fma_rn(yi, cs, -mul_rn(yr, sn)));
+}
+
+// band-edge error and FLL loop update from the finished P/Q chains of one output (fll.cpp:143-145)
+__device__ __forceinline__ void fll_update(const LoopConsts& lc, float pr, float pi, float qr, float qi, float& fph, float& ffr) {
+    const float hbe = fast_amplitude(sub_rn(pr, qi), add_rn(pi, qr));
+    const float lbe = fast_amplitude(add_rn(pr, qi), sub_rn(pi, qr));
+    const float ferr = sub_rn(hbe, lbe);
+    ffr = clampf(fma_rn(lc.fll_beta, ferr, ffr), lc.fll_min, lc.fll_max);
+    fph = wrap_pi(add_rn(fph, ffr));
 }
 
 // ---------------------------------------------------------------------------------------
@@ -227,6 +276,8 @@ __global__ void __launch_bounds__(128) demod_tpc_kernel(const __grid_constant__ 
     float2 cur[T], nxt[T];
 #pragma unroll
     for (int i = 0; i < T; ++i) { cur[i] = (i < count) ? __ldg(in + i) : make_float2(0.f, 0.f); }
+    const SymConsts kc = load_sym_consts(p);
+    const LoopConsts lc = load_loop_consts(p);
 
     int slot = 0;
 #pragma unroll 1
@@ -285,16 +336,8 @@ __global__ void __launch_bounds__(128) demod_tpc_kernel(const __grid_constant__ 
         // register file shifts down by one (positions past T-1-i hold don't-care values).
 #pragma unroll 1
         for (int i = 0; i < valid; ++i) {
-            // FastAGC [A.3]
-            const float yr = mul_rn(cur[0].x, g), yi = mul_rn(cur[0].y, g);
-            const float amp = __fsqrt_rn(fma_rn(yr, yr, mul_rn(yi, yi)));
-            g = fma_rn(sub_rn(p.agc_set_point, amp), p.agc_rate, g);
-            if (g > p.agc_max_gain) { g = p.agc_max_gain; }
-            // FLL de-rotation, fll.cpp:137-138
-            float sn, cs;
-            sincos_canon(fph, sn, cs);
-            const float xr = fma_rn(yr, cs, mul_rn(yi, sn));
-            const float xi = fma_rn(yi, cs, -mul_rn(yr, sn));
+            const float2 xv = agc_derotate(lc, cur[0], g, fph);
+            const float xr = xv.x, xi = xv.y;
             xs[(slot * T + i) * 32 + lane] = make_float2(xr, xi);
 #pragma unroll
             for (int q = 0; q < T; ++q) {
@@ -305,12 +348,7 @@ __global__ void __launch_bounds__(128) demod_tpc_kernel(const __grid_constant__ 
                 acc[q][4] = fma_rn(p.rrc[kHist - q], xr, acc[q][4]);
                 acc[q][5] = fma_rn(p.rrc[kHist - q], xi, acc[q][5]);
             }
-            // band-edge error and loop update, fll.cpp:143-145
-            const float hbe = fast_amplitude(sub_rn(acc[0][0], acc[0][3]), add_rn(acc[0][1], acc[0][2]));
-            const float lbe = fast_amplitude(add_rn(acc[0][0], acc[0][3]), sub_rn(acc[0][1], acc[0][2]));
-            const float ferr = sub_rn(hbe, lbe);
-            ffr = clampf(fma_rn(p.fll_beta, ferr, ffr), p.fll_min_freq, p.fll_max_freq);
-            fph = wrap_pi(add_rn(fph, ffr));
+            fll_update(lc, acc[0][0], acc[0][1], acc[0][2], acc[0][3], fph, ffr);
             // matched-filter output -> interpolator ring
             rs[((kITaps - 1 + n0 + i) & (RE - 1)) * 32 + lane] = make_float2(acc[0][4], acc[0][5]);
 #pragma unroll
@@ -322,7 +360,7 @@ __global__ void __launch_bounds__(128) demod_tpc_kernel(const __grid_constant__ 
         }
 
         // ---- symbols that became computable in this block (complex_fd.cpp:96 `while (offset < count)`)
-        while (st.offset < n0 + valid) { do_symbol<RE>(p, bank_s, rs, lane, st, err_blocks, active, out_base); }
+        while (st.offset < n0 + valid) { do_symbol<RE>(p, kc, bank_s, rs, lane, st, err_blocks, active, out_base); }
 
         slot = (slot + 1 == S) ? 0 : slot + 1;
 #pragma unroll
@@ -408,15 +446,15 @@ struct WsSmem {
 
 // two chains (re, im) of one real-tap filter for the T outputs of block b, over x-ring blocks
 // [first, first+nblocks) in linear-q block units; table row tp is padded with T-1 leading zeros
-template <int NB>
-__device__ __forceinline__ void ws_fir_blocks(const float* __restrict__ tp, const float2 (*xs)[32], int lane,
+template <int NB, int F>
+__device__ __forceinline__ void ws_fir_blocks(const DemodParams& p, const float2 (*xs)[32], int lane,
                                               int qblock0, float (&acc)[kWsT][2]) {
     constexpr int T = kWsT;
 #pragma unroll 1
     for (int s = 0; s < NB; ++s) {
         float tt[2 * T - 1];
 #pragma unroll
-        for (int c = 0; c < 2 * T - 1; ++c) { tt[c] = tp[s * T + c]; }
+        for (int c = 0; c < 2 * T - 1; ++c) { tt[c] = p.tpad[F][s * T + c]; }   // uniform: F is compile time
         const int slot = (qblock0 + s) & (kWsXSlots - 1);
 #pragma unroll
         for (int j = 0; j < T; ++j) {
@@ -470,10 +508,18 @@ __global__ void __launch_bounds__(160) demod_ws_kernel(const __grid_constant__ D
     SymbolState st;
     float err_blocks[TDM_SYNC_BLOCKS];
     const long long out_base = (long long)ch * p.out_stride;
+    LoopConsts lc = {};
+    SymConsts kc = {};
+    float tria[T], trib[T];                 // taps 64-q of the band-edge pair: the newest terms, in registers
+#pragma unroll
+    for (int q = 0; q < T; ++q) { tria[q] = 0.f; trib[q] = 0.f; }
     if (role == 0) {
         g = sp->agc_gain; fph = sp->fll_phase; ffr = sp->fll_freq;
 #pragma unroll
         for (int i = 0; i < T; ++i) { cur[i] = (i < count) ? __ldg(in + i) : make_float2(0.f, 0.f); }
+        lc = load_loop_consts(p);
+#pragma unroll
+        for (int q = 0; q < T; ++q) { tria[q] = pin(p.be_a[kHist - q]); trib[q] = pin(p.be_b[kHist - q]); }
     }
     if (role == 4) {
         st.mu = sp->tr_mu; st.om = sp->tr_omega; st.offset = sp->tr_offset;
@@ -483,10 +529,12 @@ __global__ void __launch_bounds__(160) demod_ws_kernel(const __grid_constant__ D
         st.nsym = 0;
 #pragma unroll
         for (int j = 0; j < TDM_SYNC_BLOCKS; ++j) { err_blocks[j] = sp->err_blocks[j]; }
+        kc = load_sym_consts(p);
     }
     __syncthreads();
 
 #ifdef TDM_ROLE_TIMING
+    long long aux_cycles = 0;
     long long work_cycles = 0;
     const long long t_begin = clock64();
 #endif
@@ -535,29 +583,23 @@ __global__ void __launch_bounds__(160) demod_ws_kernel(const __grid_constant__ D
                 }
                 // ... then the block's own samples inside the recurrence (shift-register form)
                 const int xslot = (t + 8) & (kWsXSlots - 1);
+#ifdef TDM_ROLE_TIMING
+                const long long c1 = clock64();
+                aux_cycles += c1 - c0;
+#endif
 #pragma unroll 1
                 for (int i = 0; i < valid; ++i) {
-                    const float yr = mul_rn(cur[0].x, g), yi = mul_rn(cur[0].y, g);
-                    const float amp = __fsqrt_rn(fma_rn(yr, yr, mul_rn(yi, yi)));
-                    g = fma_rn(sub_rn(p.agc_set_point, amp), p.agc_rate, g);
-                    if (g > p.agc_max_gain) { g = p.agc_max_gain; }
-                    float sn, cs;
-                    sincos_canon(fph, sn, cs);
-                    const float xr = fma_rn(yr, cs, mul_rn(yi, sn));
-                    const float xi = fma_rn(yi, cs, -mul_rn(yr, sn));
+                    const float2 xv = agc_derotate(lc, cur[0], g, fph);
+                    const float xr = xv.x, xi = xv.y;
                     sm.xs[xslot * T + i][lane] = make_float2(xr, xi);
 #pragma unroll
                     for (int q = 0; q < T; ++q) {
-                        acc[q][0] = fma_rn(p.be_a[kHist - q], xr, acc[q][0]);
-                        acc[q][1] = fma_rn(p.be_a[kHist - q], xi, acc[q][1]);
-                        acc[q][2] = fma_rn(p.be_b[kHist - q], xr, acc[q][2]);
-                        acc[q][3] = fma_rn(p.be_b[kHist - q], xi, acc[q][3]);
+                        acc[q][0] = fma_rn(tria[q], xr, acc[q][0]);
+                        acc[q][1] = fma_rn(tria[q], xi, acc[q][1]);
+                        acc[q][2] = fma_rn(trib[q], xr, acc[q][2]);
+                        acc[q][3] = fma_rn(trib[q], xi, acc[q][3]);
                     }
-                    const float hbe = fast_amplitude(sub_rn(acc[0][0], acc[0][3]), add_rn(acc[0][1], acc[0][2]));
-                    const float lbe = fast_amplitude(add_rn(acc[0][0], acc[0][3]), sub_rn(acc[0][1], acc[0][2]));
-                    const float ferr = sub_rn(hbe, lbe);
-                    ffr = clampf(fma_rn(p.fll_beta, ferr, ffr), p.fll_min_freq, p.fll_max_freq);
-                    fph = wrap_pi(add_rn(fph, ffr));
+                    fll_update(lc, acc[0][0], acc[0][1], acc[0][2], acc[0][3], fph, ffr);
 #pragma unroll
                     for (int q = 0; q < T - 1; ++q) {
 #pragma unroll
@@ -575,7 +617,8 @@ __global__ void __launch_bounds__(160) demod_ws_kernel(const __grid_constant__ D
                 float acc[T][2];
 #pragma unroll
                 for (int i = 0; i < T; ++i) { acc[i][0] = 0.f; acc[i][1] = 0.f; }
-                ws_fir_blocks<kWsFar>(p.tpad[role - 1], sm.xs, lane, b, acc);
+                if (role == 1) { ws_fir_blocks<kWsFar, 0>(p, sm.xs, lane, b, acc); }
+                else { ws_fir_blocks<kWsFar, 1>(p, sm.xs, lane, b, acc); }
                 float2 (*dst)[32] = (role == 1) ? sm.pfar[b & 1] : sm.qfar[b & 1];
 #pragma unroll
                 for (int i = 0; i < T; ++i) { dst[i][lane] = make_float2(acc[i][0], acc[i][1]); }
@@ -587,7 +630,7 @@ __global__ void __launch_bounds__(160) demod_ws_kernel(const __grid_constant__ D
                 float acc[T][2];
 #pragma unroll
                 for (int i = 0; i < T; ++i) { acc[i][0] = 0.f; acc[i][1] = 0.f; }
-                ws_fir_blocks<kWsFar + 2>(p.tpad[2], sm.xs, lane, b, acc);
+                ws_fir_blocks<kWsFar + 2, 2>(p, sm.xs, lane, b, acc);
 #pragma unroll
                 for (int i = 0; i < T; ++i) {
                     sm.rs[(kITaps - 1 + b * T + i) & (kWsREntries - 1)][lane] = make_float2(acc[i][0], acc[i][1]);
@@ -598,7 +641,7 @@ __global__ void __launch_bounds__(160) demod_ws_kernel(const __grid_constant__ D
             if (t >= 2) {
                 const int lim = min(count, (t - 1) * T);
                 while (st.offset < lim) {
-                    do_symbol<kWsREntries>(p, sm.bank, &sm.rs[0][0], lane, st, err_blocks, active, out_base);
+                    do_symbol<kWsREntries>(p, kc, sm.bank, &sm.rs[0][0], lane, st, err_blocks, active, out_base);
                 }
             }
         }
@@ -609,8 +652,8 @@ __global__ void __launch_bounds__(160) demod_ws_kernel(const __grid_constant__ D
     }
 #ifdef TDM_ROLE_TIMING
     if (blockIdx.x == 3 && lane == 0) {
-        printf("role %d: work %lld of %lld cycles (%.1f%%), per tick %lld\n", role, work_cycles, clock64() - t_begin,
-               100.0 * work_cycles / (double)(clock64() - t_begin), work_cycles / (nblk + 3));
+        printf("role %d: work %lld of %lld cycles (%.1f%%), per tick %lld (before sample loop: %lld)\n", role, work_cycles, clock64() - t_begin,
+               100.0 * work_cycles / (double)(clock64() - t_begin), work_cycles / (nblk + 3), aux_cycles / (nblk + 3));
     }
 #endif
 
@@ -656,6 +699,310 @@ int launch_ws(const DemodParams& p_in, cudaStream_t stream) {
 }
 
 // ---------------------------------------------------------------------------------------
+// Variant ws8b: the ws8 pipeline after profiling it (profiles/r01_*):
+//   * SYM was the slowest role (two serial recurrences in one warp): split into TIMING (interpolator +
+//     timing loop) and COSTAS (carrier loop + slicer + decoder), one tick apart, linked by a 16-symbol ring;
+//   * LOOP's AGC recurrence (through an IEEE sqrt) started late in each iteration, behind the FLL code in
+//     program order (the SM issues in order): the gain product of sample i+1 is now formed in iteration
+//     i, so both recurrences start at the top of the body; the 15+15 taps that meet the previous
+//     block's samples live in registers and that part is straight-line code;
+//   * the FIR roles double-buffer their tap/sample loads so no iteration starts by waiting on LDCU/LDS.
+// 6 warps: 0 LOOP, 1 P-far, 2 Q-far, 3 RRC, 4 TIMING, 5 COSTAS.
+// ---------------------------------------------------------------------------------------
+constexpr int kYRing = 16;
+struct Ws2Smem {
+    float bank[kIPhases * kITaps];
+    float2 xs[kWsXEntries][32];
+    float2 rs[kWsREntries][32];
+    float2 pfar[2][kWsT][32];
+    float2 qfar[2][kWsT][32];
+    float2 ys[kYRing][32];
+    int ycount[2][32];
+};
+
+template <int NB, int F>
+__device__ __forceinline__ void ws_fir_blocks2(const DemodParams& p, const float2 (*xs)[32], int lane,
+                                               int qblock0, float (&acc)[kWsT][2]) {
+    constexpr int T = kWsT;
+    float ta[2 * T - 1], tb[2 * T - 1];
+    float2 ha[T], hb[T];
+    auto load = [&](float (&tt)[2 * T - 1], float2 (&h)[T], int s) {
+#pragma unroll
+        for (int c = 0; c < 2 * T - 1; ++c) { tt[c] = p.tpad[F][s * T + c]; }
+        const int slot = (qblock0 + s) & (kWsXSlots - 1);
+#pragma unroll
+        for (int j = 0; j < T; ++j) { h[j] = xs[slot * T + j][lane]; }
+    };
+    auto comp = [&](const float (&tt)[2 * T - 1], const float2 (&h)[T]) {
+#pragma unroll
+        for (int j = 0; j < T; ++j) {
+#pragma unroll
+            for (int i = 0; i < T; ++i) {
+                acc[i][0] = fma_rn(tt[j - i + T - 1], h[j].x, acc[i][0]);
+                acc[i][1] = fma_rn(tt[j - i + T - 1], h[j].y, acc[i][1]);
+            }
+        }
+    };
+    load(ta, ha, 0);
+#pragma unroll 1
+    for (int s = 0; s + 1 < NB; s += 2) {
+        load(tb, hb, s + 1);
+        comp(ta, ha);
+        load(ta, ha, s + 2);        // one block past the end on the last trip when NB is even: in-bounds, unused
+        comp(tb, hb);
+    }
+    if (NB & 1) { comp(ta, ha); }
+}
+
+__global__ void __launch_bounds__(192) demod_ws2_kernel(const __grid_constant__ DemodParams p) {
+    constexpr int T = kWsT;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    Ws2Smem& sm = *reinterpret_cast<Ws2Smem*>(smem_raw);
+    const int lane = threadIdx.x & 31;
+    const int role = threadIdx.x >> 5;
+
+    for (int i = threadIdx.x; i < kIPhases * kITaps; i += blockDim.x) { sm.bank[i] = p.bank[i]; }
+    for (int i = threadIdx.x; i < (kWsXEntries - kHist) * 32; i += blockDim.x) {
+        sm.xs[kHist + i / 32][i % 32] = make_float2(0.f, 0.f);     // see demod_ws_kernel: zero taps must meet finite data
+    }
+    if (threadIdx.x < 64) { sm.ycount[threadIdx.x >> 5][lane] = 0; }
+
+    int ch = blockIdx.x * 32 + lane;
+    const bool active = ch < p.n_channels;
+    if (!active) { ch = p.n_channels - 1; }
+    tdm_channel_state* __restrict__ sp = p.states + ch;
+    const int count = p.count;
+    const int nblk = (count + T - 1) / T;
+    if (role == 1) {
+        const float2* xh = reinterpret_cast<const float2*>(sp->x_hist);
+        for (int m = 0; m < kHist; ++m) { sm.xs[m][lane] = xh[m]; }
+    }
+    if (role == 3) {
+        const float2* rh = reinterpret_cast<const float2*>(sp->r_hist);
+        for (int j = 0; j < kITaps - 1; ++j) { sm.rs[j][lane] = rh[j]; }
+    }
+
+    // ---- role-private state
+    float g = 0.f, fph = 0.f, ffr = 0.f, yr = 0.f, yi = 0.f;
+    float2 cur[T], nxt[T];
+    const float2* __restrict__ in = p.iq + (long long)ch * p.in_stride;
+    LoopConsts lc = {};
+    float tria[T], trib[T], mida[2 * T - 1], midb[2 * T - 1];
+    if (role == 0) {
+        g = sp->agc_gain; fph = sp->fll_phase; ffr = sp->fll_freq;
+#pragma unroll
+        for (int i = 0; i < T; ++i) { cur[i] = (i < count) ? __ldg(in + i) : make_float2(0.f, 0.f); }
+        lc = load_loop_consts(p);
+#pragma unroll
+        for (int q = 0; q < T; ++q) { tria[q] = pin(p.be_a[kHist - q]); trib[q] = pin(p.be_b[kHist - q]); }
+#pragma unroll
+        for (int c = 0; c < 2 * T - 1; ++c) { mida[c] = pin(p.be_a[kHist - 2 * T + 1 + c]); midb[c] = pin(p.be_b[kHist - 2 * T + 1 + c]); }
+        yr = mul_rn(cur[0].x, g); yi = mul_rn(cur[0].y, g);
+    }
+    SymConsts kc = {};
+    float mu = 0.f, om = 0.f;
+    int offset = 0, nsym_t = 0;
+    if (role == 4) {
+        mu = sp->tr_mu; om = sp->tr_omega; offset = sp->tr_offset;
+        kc = load_sym_consts(p);
+    }
+    SymbolState st;
+    float err_blocks[TDM_SYNC_BLOCKS];
+    const long long out_base = (long long)ch * p.out_stride;
+    if (role == 5) {
+        st.mu = 0.f; st.om = 0.f; st.offset = 0;
+        st.cph = sp->costas_phase; st.cfr = sp->costas_freq; st.ph2 = sp->costas_ph2;
+        st.prev = sp->prev_sym; st.err_ptr = sp->err_ptr; st.err_disp = sp->err_disp;
+        st.err_partial = sp->err_partial; st.standarderr = sp->standarderr; st.sync = sp->sync;
+        st.nsym = 0;
+#pragma unroll
+        for (int j = 0; j < TDM_SYNC_BLOCKS; ++j) { err_blocks[j] = sp->err_blocks[j]; }
+        kc = load_sym_consts(p);
+    }
+    __syncthreads();
+
+#ifdef TDM_ROLE_TIMING
+    long long aux_cycles = 0, work_cycles = 0;
+    const long long t_begin = clock64();
+#endif
+#pragma unroll 1
+    for (int t = -1; t <= nblk + 2; ++t) {
+#ifdef TDM_ROLE_TIMING
+        const long long c0 = clock64();
+#endif
+        if (role == 0) {
+            // ================= LOOP: block b = t =================
+            if (t >= 0 && t < nblk) {
+                const int n0 = t * T;
+                const int valid = min(T, count - n0);
+#pragma unroll
+                for (int i = 0; i < T; ++i) {
+                    const int n = n0 + T + i;
+                    nxt[i] = (n < count) ? __ldg(in + n) : make_float2(0.f, 0.f);
+                }
+                float acc[T][4];
+#pragma unroll
+                for (int i = 0; i < T; ++i) {
+                    const float2 pf = sm.pfar[t & 1][i][lane], qf = sm.qfar[t & 1][i][lane];
+                    acc[i][0] = pf.x; acc[i][1] = pf.y; acc[i][2] = qf.x; acc[i][3] = qf.y;
+                }
+                {   // previous block's 8 samples: taps 56 + j - i = mid[7 + j - i]
+                    const int slot = (t + 7) & (kWsXSlots - 1);
+                    float2 h[T];
+#pragma unroll
+                    for (int j = 0; j < T; ++j) { h[j] = sm.xs[slot * T + j][lane]; }
+#pragma unroll
+                    for (int j = 0; j < T; ++j) {
+#pragma unroll
+                        for (int i = 0; i < T; ++i) {
+                            acc[i][0] = fma_rn(mida[T - 1 + j - i], h[j].x, acc[i][0]);
+                            acc[i][1] = fma_rn(mida[T - 1 + j - i], h[j].y, acc[i][1]);
+                            acc[i][2] = fma_rn(midb[T - 1 + j - i], h[j].x, acc[i][2]);
+                            acc[i][3] = fma_rn(midb[T - 1 + j - i], h[j].y, acc[i][3]);
+                        }
+                    }
+                }
+                const int xslot = (t + 8) & (kWsXSlots - 1);
+#ifdef TDM_ROLE_TIMING
+                aux_cycles += clock64() - c0;
+#endif
+#pragma unroll 1
+                for (int i = 0; i < valid; ++i) {
+                    // FLL recurrence on the already-scaled sample y = in * g
+                    float sn, cs;
+                    sincos_canon(fph, sn, cs);
+                    const float xr = fma_rn(yr, cs, mul_rn(yi, sn));
+                    const float xi = fma_rn(yi, cs, -mul_rn(yr, sn));
+                    sm.xs[xslot * T + i][lane] = make_float2(xr, xi);
+#pragma unroll
+                    for (int q = 0; q < T; ++q) {
+                        acc[q][0] = fma_rn(tria[q], xr, acc[q][0]);
+                        acc[q][1] = fma_rn(tria[q], xi, acc[q][1]);
+                        acc[q][2] = fma_rn(trib[q], xr, acc[q][2]);
+                        acc[q][3] = fma_rn(trib[q], xi, acc[q][3]);
+                    }
+                    fll_update(lc, acc[0][0], acc[0][1], acc[0][2], acc[0][3], fph, ffr);
+                    // AGC recurrence, one sample ahead: gain after this sample, then the next sample's product
+                    const float amp = sqrt_rn_nobranch(fma_rn(yr, yr, mul_rn(yi, yi)));
+                    g = fma_rn(sub_rn(lc.agc_set, amp), lc.agc_rate, g);
+                    g = g > lc.agc_max ? lc.agc_max : g;
+#pragma unroll
+                    for (int q = 0; q < T - 1; ++q) {
+#pragma unroll
+                        for (int c = 0; c < 4; ++c) { acc[q][c] = acc[q + 1][c]; }
+                        cur[q] = cur[q + 1];
+                    }
+                    yr = mul_rn(cur[0].x, g); yi = mul_rn(cur[0].y, g);
+                }
+#pragma unroll
+                for (int i = 0; i < T; ++i) { cur[i] = nxt[i]; }
+                yr = mul_rn(cur[0].x, g); yi = mul_rn(cur[0].y, g);
+            }
+        } else if (role == 1 || role == 2) {
+            // ================= P-far / Q-far: block b = t + 1 =================
+            const int b = t + 1;
+            if (b < nblk) {
+                float acc[T][2];
+#pragma unroll
+                for (int i = 0; i < T; ++i) { acc[i][0] = 0.f; acc[i][1] = 0.f; }
+                if (role == 1) { ws_fir_blocks2<kWsFar, 0>(p, sm.xs, lane, b, acc); }
+                else { ws_fir_blocks2<kWsFar, 1>(p, sm.xs, lane, b, acc); }
+                float2 (*dst)[32] = (role == 1) ? sm.pfar[b & 1] : sm.qfar[b & 1];
+#pragma unroll
+                for (int i = 0; i < T; ++i) { dst[i][lane] = make_float2(acc[i][0], acc[i][1]); }
+            }
+        } else if (role == 3) {
+            // ================= RRC: block b = t - 1 =================
+            const int b = t - 1;
+            if (b >= 0 && b < nblk) {
+                float acc[T][2];
+#pragma unroll
+                for (int i = 0; i < T; ++i) { acc[i][0] = 0.f; acc[i][1] = 0.f; }
+                ws_fir_blocks2<kWsFar + 2, 2>(p, sm.xs, lane, b, acc);
+#pragma unroll
+                for (int i = 0; i < T; ++i) {
+                    sm.rs[(kITaps - 1 + b * T + i) & (kWsREntries - 1)][lane] = make_float2(acc[i][0], acc[i][1]);
+                }
+            }
+        } else if (role == 4) {
+            // ================= TIMING: symbols whose newest input sample lies in block t - 2 =================
+            if (t >= 2) {
+                const int lim = min(count, (t - 1) * T);
+                while (offset < lim) {
+                    const float2 y = timing_step<kWsREntries>(kc, sm.bank, &sm.rs[0][0], lane, mu, om, offset);
+                    sm.ys[nsym_t & (kYRing - 1)][lane] = y;
+                    ++nsym_t;
+                }
+                sm.ycount[t & 1][lane] = nsym_t;
+            }
+        } else {
+            // ================= COSTAS: the symbols TIMING finished during tick t - 1 =================
+            if (t >= 3) {
+                const int target = sm.ycount[(t - 1) & 1][lane];
+                while (st.nsym < target) {
+                    const float2 y = sm.ys[st.nsym & (kYRing - 1)][lane];
+                    costas_step(p, kc, y, st, err_blocks, active, out_base);
+                }
+            }
+        }
+#ifdef TDM_ROLE_TIMING
+        work_cycles += clock64() - c0;
+#endif
+        __syncthreads();
+    }
+#ifdef TDM_ROLE_TIMING
+    if (blockIdx.x == 3 && lane == 0) {
+        unsigned wid, smid;
+        asm volatile("mov.u32 %0, %%warpid;" : "=r"(wid));
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        printf("role %d (hw warp slot %u on SM %u): work %lld of %lld cycles (%.1f%%), per tick %lld (before sample loop: %lld)\n", role, wid, smid, work_cycles,
+               clock64() - t_begin, 100.0 * work_cycles / (double)(clock64() - t_begin), work_cycles / (nblk + 4), aux_cycles / (nblk + 4));
+    }
+#endif
+
+    // ---- carry state out
+    if (!active) { return; }
+    if (role == 0) {
+        sp->agc_gain = g; sp->fll_phase = fph; sp->fll_freq = ffr;
+        sp->n_samples += (unsigned long long)count;
+    } else if (role == 1) {
+        float2* xh = reinterpret_cast<float2*>(sp->x_hist);
+        for (int m = 0; m < kHist; ++m) {
+            const long long q = (long long)count + m;
+            xh[m] = sm.xs[(int)((q / T) & (kWsXSlots - 1)) * T + (int)(q % T)][lane];
+        }
+    } else if (role == 3) {
+        float2* rh = reinterpret_cast<float2*>(sp->r_hist);
+        for (int j = 0; j < kITaps - 1; ++j) { rh[j] = sm.rs[(count + j) & (kWsREntries - 1)][lane]; }
+    } else if (role == 4) {
+        sp->tr_mu = mu; sp->tr_omega = om; sp->tr_offset = offset - count;
+    } else if (role == 5) {
+        sp->costas_phase = st.cph; sp->costas_freq = st.cfr; sp->costas_ph2 = st.ph2;
+        sp->prev_sym = st.prev; sp->err_ptr = st.err_ptr; sp->err_disp = st.err_disp;
+        sp->err_partial = st.err_partial; sp->standarderr = st.standarderr; sp->sync = st.sync;
+        sp->n_symbols += (unsigned long long)st.nsym;
+#pragma unroll
+        for (int j = 0; j < TDM_SYNC_BLOCKS; ++j) { sp->err_blocks[j] = err_blocks[j]; }
+        p.out_counts[ch] = st.nsym;
+    }
+}
+
+int launch_ws2(const DemodParams& p_in, cudaStream_t stream) {
+    DemodParams p = p_in;
+    const float* src[3] = { p.be_a, p.be_b, p.rrc };
+    for (int f = 0; f < 3; ++f) {
+        for (int j = 0; j < kTapPad; ++j) {
+            const int k = j - (kWsT - 1);
+            p.tpad[f][j] = (k >= 0 && k < kTaps) ? src[f][k] : 0.f;
+        }
+    }
+    cudaFuncSetAttribute(demod_ws2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Ws2Smem));
+    const int grid = (p.n_channels + 31) / 32;
+    demod_ws2_kernel<<<grid, 192, sizeof(Ws2Smem), stream>>>(p);
+    return cudaGetLastError() == cudaSuccess ? 1 : -1;
+}
+
+// ---------------------------------------------------------------------------------------
 // dibit packing for the multi-GPU gather: 4 symbols per byte, first symbol in bits 7..6.
 // ---------------------------------------------------------------------------------------
 __global__ void pack_dibits_kernel(const uint8_t* __restrict__ dibits, long long in_stride,
@@ -686,18 +1033,23 @@ const char* demod_variant_name(int variant) {
         case 2: return "tpc8";
         case 3: return "tpc4x4";
         case 4: return "ws8";
+        case 5: return "ws8b";
         default: return "auto";
     }
 }
 
 int launch_demod(const DemodParams& p, int variant, cudaStream_t stream) {
     if (p.n_channels <= 0) { return 0; }
-    if (variant == 0) { variant = 1; }
+    // auto: the warp-specialised pipeline wins while channels are scarce (it puts 6 warps behind every 32
+    // channels); once there are enough channels to fill every scheduler with plain thread-per-channel warps,
+    // the monolithic kernel's lower instruction count wins.
+    if (variant == 0) { variant = (p.n_channels >= 16384) ? 2 : 5; }
     switch (variant) {
         case 1: return launch_tpc<4>(p, stream, 1);
         case 2: return launch_tpc<8>(p, stream, 1);
         case 3: return launch_tpc<4>(p, stream, 4);
         case 4: return launch_ws(p, stream);
+        case 5: return launch_ws2(p, stream);
         default: return -1;
     }
 }

@@ -27,7 +27,7 @@ if __name__ == "__main__":
     print(torch.cuda.get_device_name(0))
     res = []
     for (C_, N) in [(4096, 32768), (512, 65536), (256, 65536), (32768, 8192)]:
-        for v in [2, 4]:
+        for v in [2, 4, 5]:
             ms, cnt, m = timeit(C_, N, v)
             gs = C_ * N / ms / 1e6
             print(f"C={C_} N={N} variant={v}: {ms:.2f} ms  {gs:.2f} Gsamples/s  {gs*8/6492.4*100:.2f}% HBM  mean syms {cnt.mean():.1f} sync {m['sync'].mean():.2f}")
