@@ -754,12 +754,18 @@ __device__ __forceinline__ void ws_fir_blocks2(const DemodParams& p, const float
     if (NB & 1) { comp(ta, ha); }
 }
 
-__global__ void __launch_bounds__(192) demod_ws2_kernel(const __grid_constant__ DemodParams p) {
+// WARPS = 6: roles on consecutive warps.  WARPS = 8: two idle warps, placed so that (with the hardware's
+// warp-slot -> scheduler mapping observed on B200, scheduler = (warp+1) & 3) LOOP has a scheduler to itself,
+// P-far shares with TIMING, Q-far with COSTAS, RRC is alone.
+template <int WARPS>
+__global__ void __launch_bounds__(WARPS * 32) demod_ws2_kernel(const __grid_constant__ DemodParams p) {
     constexpr int T = kWsT;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     Ws2Smem& sm = *reinterpret_cast<Ws2Smem*>(smem_raw);
     const int lane = threadIdx.x & 31;
-    const int role = threadIdx.x >> 5;
+    const int warp = threadIdx.x >> 5;
+    // warp -> role (6 = idle)
+    const int role = (WARPS == 6) ? warp : (warp == 0 ? 0 : warp == 1 ? 1 : warp == 2 ? 2 : warp == 3 ? 3 : warp == 5 ? 4 : warp == 6 ? 5 : 6);
 
     for (int i = threadIdx.x; i < kIPhases * kITaps; i += blockDim.x) { sm.bank[i] = p.bank[i]; }
     for (int i = threadIdx.x; i < (kWsXEntries - kHist) * 32; i += blockDim.x) {
@@ -924,6 +930,8 @@ __global__ void __launch_bounds__(192) demod_ws2_kernel(const __grid_constant__ 
                     sm.rs[(kITaps - 1 + b * T + i) & (kWsREntries - 1)][lane] = make_float2(acc[i][0], acc[i][1]);
                 }
             }
+        } else if (role == 6) {
+            // idle warp: only keeps the barrier count
         } else if (role == 4) {
             // ================= TIMING: symbols whose newest input sample lies in block t - 2 =================
             if (t >= 2) {
@@ -987,7 +995,7 @@ __global__ void __launch_bounds__(192) demod_ws2_kernel(const __grid_constant__ 
     }
 }
 
-int launch_ws2(const DemodParams& p_in, cudaStream_t stream) {
+int launch_ws2(const DemodParams& p_in, cudaStream_t stream, int warps) {
     DemodParams p = p_in;
     const float* src[3] = { p.be_a, p.be_b, p.rrc };
     for (int f = 0; f < 3; ++f) {
@@ -996,9 +1004,14 @@ int launch_ws2(const DemodParams& p_in, cudaStream_t stream) {
             p.tpad[f][j] = (k >= 0 && k < kTaps) ? src[f][k] : 0.f;
         }
     }
-    cudaFuncSetAttribute(demod_ws2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Ws2Smem));
     const int grid = (p.n_channels + 31) / 32;
-    demod_ws2_kernel<<<grid, 192, sizeof(Ws2Smem), stream>>>(p);
+    if (warps == 8) {
+        cudaFuncSetAttribute(demod_ws2_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Ws2Smem));
+        demod_ws2_kernel<8><<<grid, 256, sizeof(Ws2Smem), stream>>>(p);
+    } else {
+        cudaFuncSetAttribute(demod_ws2_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Ws2Smem));
+        demod_ws2_kernel<6><<<grid, 192, sizeof(Ws2Smem), stream>>>(p);
+    }
     return cudaGetLastError() == cudaSuccess ? 1 : -1;
 }
 
@@ -1034,6 +1047,7 @@ const char* demod_variant_name(int variant) {
         case 3: return "tpc4x4";
         case 4: return "ws8";
         case 5: return "ws8b";
+        case 6: return "ws8b-8w";
         default: return "auto";
     }
 }
@@ -1049,7 +1063,8 @@ int launch_demod(const DemodParams& p, int variant, cudaStream_t stream) {
         case 2: return launch_tpc<8>(p, stream, 1);
         case 3: return launch_tpc<4>(p, stream, 4);
         case 4: return launch_ws(p, stream);
-        case 5: return launch_ws2(p, stream);
+        case 5: return launch_ws2(p, stream, 6);
+        case 6: return launch_ws2(p, stream, 8);
         default: return -1;
     }
 }
