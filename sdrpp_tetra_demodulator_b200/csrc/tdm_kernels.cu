@@ -1016,6 +1016,496 @@ int launch_ws2(const DemodParams& p_in, cudaStream_t stream, int warps) {
 }
 
 // ---------------------------------------------------------------------------------------
+// Variant ws3: the ws8b pipeline rebuilt around FFMA2 and a straight-line recurrence.
+//
+// What profiling ws8b showed (profiles/r01_ws8b_*): 3635 cycles per 8-sample tick against a
+// ~1000-cycle dependency floor; the LOOP warp issued ~1000 instructions per tick (64 FFMA per
+// sample for the newest terms in a rolled shift-register loop, 35 MOVs per sample to shift it),
+// the FIR warps ran at 1.38 cycles per FMA (FFMA with a uniform operand is issue limited), and
+// warps that shared a scheduler with LOOP delayed it.  Changes:
+//   * every FIR chain advances (re, im) together with FFMA2 (fma2_rn): half the issue slots, and
+//     1.15 cycles per FMA measured in isolation (tools/ubench/ubench_ffma2.cu);
+//   * LOOP's tick is ONE basic block for a full block of 8 samples: no shift register, the
+//     triangular own-block part costs 36 FFMA2 per chain pair instead of 64, and ptxas is free
+//     to sink the 128 "previous block" FFMA2 into the latency shadow of the sin/cos -> rotate ->
+//     band-edge -> loop-filter chain.  A partial last block takes the old rolled form;
+//   * the matched filter is split over two warps (outputs 0..3 / 4..7 of a block);
+//   * 8 warps, placed so that LOOP's scheduler carries nothing else (or only the lightest role);
+//   * the input is prefetched into L2 four ticks ahead and loaded one tick ahead.
+// Chains and their term order are unchanged (far -> previous block -> own block, ascending taps),
+// so the results are bit-identical to every other variant and to the canonical-order checker.
+// ---------------------------------------------------------------------------------------
+enum Ws3Role { kRLoop = 0, kRPfar = 1, kRQfar = 2, kRRrcA = 3, kRRrcB = 4, kRTiming = 5, kRCostas = 6, kRSlicer = 7 };
+
+// warp -> role.  Warps w and w+4 share a scheduler (SMSP = warp slot mod 4 up to a rotation).
+template <int PLACEMENT>
+__device__ __forceinline__ int ws3_role_of_warp(int warp) {
+    // one role per nibble, warp 0 in the lowest (a table indexed by the warp number would live in local memory)
+    constexpr unsigned r0 = kRLoop, rP = kRPfar, rQ = kRQfar, rA = kRRrcA, rB = kRRrcB, rT = kRTiming, rC = kRCostas, rS = kRSlicer;
+    constexpr unsigned tab =
+        PLACEMENT == 0 ? (r0 | rP << 4 | rQ << 8 | rA << 12 | rS << 16 | rT << 20 | rC << 24 | rB << 28)    // LOOP+SLICER; P+TIMING; Q+COSTAS; RRC A+B
+      : PLACEMENT == 1 ? (r0 | rP << 4 | rQ << 8 | rA << 12 | rB << 16 | rT << 20 | rC << 24 | rS << 28)    // LOOP+RRC-B; P+TIMING; Q+COSTAS; RRC-A+SLICER
+      :                  (r0 | rP << 4 | rQ << 8 | rA << 12 | rC << 16 | rB << 20 | rT << 24 | rS << 28);   // LOOP+COSTAS; P+RRC-B; Q+TIMING; RRC-A+SLICER
+    return (int)((tab >> (4 * warp)) & 0xfu);
+}
+
+// (re, im) chains of one real-tap filter for NI consecutive outputs of a block, over NB x-ring blocks
+// starting at linear block qblock0.  Row f of tpad (T-1 leading zeros) holds the taps; c0 = T - 1 - (last
+// output index) is the lowest table column this output range meets.  f and c0 are RUN-TIME (warp-uniform)
+// values on purpose: P-far and Q-far, and the two matched-filter halves, then execute the same instructions,
+// which keeps the kernel's hot code inside the instruction cache.
+template <int NB, int NI>
+__device__ __forceinline__ void ws3_fir_blocks(const DemodParams& p, const float2 (*xs)[32], int lane,
+                                               int qblock0, int f, int c0, float2 (&acc)[NI]) {
+    constexpr int T = kWsT;
+    constexpr int NC = T + NI - 1;                     // columns met: j - i + NI - 1 for j < T, i < NI
+    float ta[NC], tb[NC];
+    float2 ha[T], hb[T];
+    const float* __restrict__ row = p.tpad[0] + f * kTapPad + c0;
+    auto load = [&](float (&tt)[NC], float2 (&h)[T], int s) {
+#pragma unroll
+        for (int c = 0; c < NC; ++c) { tt[c] = row[s * T + c]; }
+        const int slot = (qblock0 + s) & (kWsXSlots - 1);
+#pragma unroll
+        for (int j = 0; j < T; ++j) { h[j] = xs[slot * T + j][lane]; }
+    };
+    auto comp = [&](const float (&tt)[NC], const float2 (&h)[T]) {
+#pragma unroll
+        for (int j = 0; j < T; ++j) {
+#pragma unroll
+            for (int i = 0; i < NI; ++i) { acc[i] = fma2_rn(tt[j - i + NI - 1], h[j], acc[i]); }
+        }
+    };
+    load(ta, ha, 0);
+#pragma unroll 1
+    for (int s = 0; s + 1 < NB; s += 2) {
+        load(tb, hb, s + 1);
+        comp(ta, ha);
+        load(ta, ha, s + 2);        // one block past the end on the last trip when NB is even: in-bounds, unused
+        comp(tb, hb);
+    }
+    if (NB & 1) { comp(ta, ha); }
+}
+
+// timing_step with the three interpolator chains advanced pairwise by FFMA2 (same terms, same order).
+template <int RE>
+__device__ __forceinline__ float2 timing_step2(const SymConsts& kc, const float* __restrict__ bank_s,
+                                               const float2* rs, int lane, float& mu, float& om, int& offset) {
+    const float phf = fminf(fmaxf(floorf(mul_rn(mu, (float)kIPhases)), 0.0f), (float)(kIPhases - 1));   // see timing_step
+    const int ph = (int)phf;
+    const int plo = max(ph - 1, 0);
+    const int phi = min(ph + 1, kIPhases - 1);
+    const float4* r0 = reinterpret_cast<const float4*>(bank_s + ph * kITaps);
+    const float4* r1 = reinterpret_cast<const float4*>(bank_s + phi * kITaps);
+    const float4* r2 = reinterpret_cast<const float4*>(bank_s + plo * kITaps);
+    const float4 t0a = r0[0], t0b = r0[1], t1a = r1[0], t1b = r1[1], t2a = r2[0], t2b = r2[1];
+    const float t0[8] = { t0a.x, t0a.y, t0a.z, t0a.w, t0b.x, t0b.y, t0b.z, t0b.w };
+    const float t1[8] = { t1a.x, t1a.y, t1a.z, t1a.w, t1b.x, t1b.y, t1b.z, t1b.w };
+    const float t2[8] = { t2a.x, t2a.y, t2a.z, t2a.w, t2b.x, t2b.y, t2b.z, t2b.w };
+    float2 y = make_float2(0.f, 0.f), a = make_float2(0.f, 0.f), b = make_float2(0.f, 0.f);
+#pragma unroll
+    for (int k = 0; k < kITaps; ++k) {
+        const float2 v = rs[((offset + k) & (RE - 1)) * 32 + lane];
+        y = fma2_rn(t0[k], v, y);
+        a = fma2_rn(t1[k], v, a);
+        b = fma2_rn(t2[k], v, b);
+    }
+    const float dscale = (phi - plo == 2) ? 0.5f : 1.0f;
+    const float dre = mul_rn(sub_rn(a.x, b.x), dscale);
+    const float dim = mul_rn(sub_rn(a.y, b.y), dscale);
+    float terr = add_rn(y.x > 0.f ? dre : -dre, y.y > 0.f ? dim : -dim);
+    terr = clampf(terr, -1.0f, 1.0f);
+    om = clampf(fma_rn(kc.tr_beta, terr, om), kc.tr_min, kc.tr_max);
+    mu = add_rn(mu, fma_rn(kc.tr_alpha, terr, om));
+    float delta = floorf(mu);
+    delta = (delta >= 0.0f) ? delta : 1.0f;            // non-finite guard, see timing_step
+    delta = fminf(delta, 1048576.0f);
+    offset += (int)delta;
+    mu = sub_rn(mu, delta);
+    return y;
+}
+
+// The carrier-recovery half of costas_step (pi4dqpsk_costas.cpp:5-28), branch free: returns the de-rotated
+// symbol (PI4DQPSK's `out`), advances (phase, freq, ph2).  ph2's wrap forms both candidates and selects.
+__device__ __forceinline__ float2 costas_loop_step(const SymConsts& kc, float2 y, float& cph, float& cfr, float& ph2) {
+    float sn, cs;
+    sincos_canon(cph, sn, cs);
+    const float zr = fma_rn(y.x, cs, mul_rn(y.y, sn));
+    const float zi = fma_rn(y.y, cs, -mul_rn(y.x, sn));
+    const float two_pi_c = 2 * TDM_FL_M_PI;
+    const float q0 = add_rn(ph2, -(TDM_FL_M_PI / 4.0f));
+    const float qd = sub_rn(q0, two_pi_c), qu = add_rn(q0, two_pi_c);
+    const float q = (q0 >= two_pi_c) ? qd : ((q0 <= -two_pi_c) ? qu : q0);
+    ph2 = q;
+    float s2, c2;
+    sincos_canon(q, s2, c2);
+    const float ur = fma_rn(zr, c2, -mul_rn(zi, s2));
+    const float ui = fma_rn(zi, c2, mul_rn(zr, s2));
+    float cerr = sub_rn(ur > 0.f ? ui : -ui, ui > 0.f ? ur : -ur);
+    cerr = clampf(cerr, -1.0f, 1.0f);
+    cfr = clampf(fma_rn(kc.c_beta, cerr, cfr), kc.c_min, kc.c_max);
+    cph = wrap_pi(add_rn(cph, fma_rn(kc.c_alpha, cerr, cfr)));
+    return make_float2(ur, ui);
+}
+
+// The slicer half of costas_step (dqpsk_sym_extr.cpp:4-55, bit_unpacker.cpp:6-7) for the first n (<= NS)
+// symbols of ring `us` starting at symbol index sl.nsym: NS predicated copies in straight-line code, so the
+// independent per-symbol work (lock metric polynomial, decisions, address arithmetic, stores) of several
+// symbols overlaps.  The 256-symbol block rotation of the lock metric can fire at most once in NS <= 255
+// symbols: it is captured with selects and carried out once at the end (nothing in between reads it).
+struct SlicerState {
+    uint32_t prev, err_ptr, err_disp;
+    float err_partial, standarderr;
+    uint32_t sync;
+    int nsym;
+};
+template <int NS, int RING>
+__device__ __forceinline__ void slicer_symbols(const DemodParams& p, const float2 (*us)[32], int lane, int n, SlicerState& sl,
+                                               float* __restrict__ err_blocks, bool active, long long out_base) {
+    bool crossed = false;
+    float saved_partial = 0.f;
+    uint32_t saved_ptr = 0;
+    const int base = sl.nsym;
+#pragma unroll
+    for (int k = 0; k < NS; ++k) {
+        const bool v = k < n;
+        const float2 u = us[(base + k) & (RING - 1)][lane];
+        const bool a = u.y < 0.f, b = u.x < 0.f;
+        const float dist = quadrant_phase_error(u.x, u.y);     // |ideal.phase() - sym.phase()|, dqpsk_sym_extr.cpp:8-11
+        const float ep = add_rn(sl.err_partial, dist);
+        sl.err_partial = v ? ep : sl.err_partial;
+        sl.err_ptr += v ? 1u : 0u;
+        sl.err_disp += v ? 1u : 0u;
+        const bool cross = v && sl.err_disp >= TDM_SYNC_DISPLAY;
+        saved_partial = cross ? sl.err_partial : saved_partial;
+        saved_ptr = cross ? sl.err_ptr : saved_ptr;
+        crossed = crossed || cross;
+        sl.err_partial = cross ? 0.f : sl.err_partial;
+        sl.err_disp = cross ? 0u : sl.err_disp;
+        sl.err_ptr = (sl.err_ptr >= TDM_SYNC_BUF) ? 0u : sl.err_ptr;
+        const uint32_t sym = ((uint32_t)a << 1) | (uint32_t)(a != b);
+        const uint32_t pd = (sym - sl.prev + 4u) & 3u;
+        const uint32_t db = pd ^ (pd >> 1);          // 0,1,2,3 -> 0,1,3,2
+        sl.prev = v ? sym : sl.prev;
+        if (v && active && base + k < p.out_stride) {   // rows are sized by tdm_max_symbols(); never write past one
+            const long long o = out_base + base + k;
+            if (p.syms) { p.syms[o] = u; }
+            if (p.dibits) { p.dibits[o] = (uint8_t)db; }
+            if (p.bits) { reinterpret_cast<uchar2*>(p.bits)[o] = make_uchar2((uint8_t)((db >> 1) & 1u), (uint8_t)(db & 1u)); }
+        }
+    }
+    sl.nsym = base + n;
+    if (crossed) {
+        err_blocks[(saved_ptr - 1) / TDM_SYNC_DISPLAY] = saved_partial;
+        float tot = 0.f;
+#pragma unroll
+        for (int j = 0; j < TDM_SYNC_BLOCKS; ++j) { tot = add_rn(tot, err_blocks[j]); }
+        sl.standarderr = __fdiv_rn(tot, (float)TDM_SYNC_BUF);
+        sl.sync = sl.standarderr < 0.35f ? 1u : 0u;
+    }
+}
+
+constexpr int kSymRing = 16;      // >= symbols in flight between two symbol-rate roles (<= 5 per tick, two ticks)
+struct Ws3Smem {
+    float bank[kIPhases * kITaps];
+    float2 xs[kWsXEntries][32];
+    float2 rs[kWsREntries][32];
+    float2 pfar[2][kWsT][32];
+    float2 qfar[2][kWsT][32];
+    float2 ys[kSymRing][32];       // TIMING -> COSTAS: interpolated symbols
+    float2 us[kSymRing][32];       // COSTAS -> SLICER: carrier-corrected symbols
+    int ycount[2][32];
+    int ucount[2][32];
+};
+
+template <int PLACEMENT>
+__global__ void __launch_bounds__(256) demod_ws3_kernel(const __grid_constant__ DemodParams p) {
+    constexpr int T = kWsT;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    Ws3Smem& sm = *reinterpret_cast<Ws3Smem*>(smem_raw);
+    const int lane = threadIdx.x & 31;
+    const int role = ws3_role_of_warp<PLACEMENT>(threadIdx.x >> 5);
+
+    for (int i = threadIdx.x; i < kIPhases * kITaps; i += blockDim.x) { sm.bank[i] = p.bank[i]; }
+    for (int i = threadIdx.x; i < (kWsXEntries - kHist) * 32; i += blockDim.x) {
+        sm.xs[kHist + i / 32][i % 32] = make_float2(0.f, 0.f);     // see demod_ws_kernel: zero taps must meet finite data
+    }
+    if (threadIdx.x < 64) { sm.ycount[threadIdx.x >> 5][lane] = 0; sm.ucount[threadIdx.x >> 5][lane] = 0; }
+    for (int i = threadIdx.x; i < kSymRing * 32; i += blockDim.x) {
+        sm.ys[i / 32][i % 32] = make_float2(0.f, 0.f);
+        sm.us[i / 32][i % 32] = make_float2(0.f, 0.f);
+    }
+
+    int ch = blockIdx.x * 32 + lane;
+    const bool active = ch < p.n_channels;
+    if (!active) { ch = p.n_channels - 1; }
+    tdm_channel_state* __restrict__ sp = p.states + ch;
+    const int count = p.count;
+    const int nblk = (count + T - 1) / T;
+    if (role == kRPfar) {
+        const float2* xh = reinterpret_cast<const float2*>(sp->x_hist);
+        for (int m = 0; m < kHist; ++m) { sm.xs[m][lane] = xh[m]; }
+    }
+    if (role == kRRrcA) {
+        const float2* rh = reinterpret_cast<const float2*>(sp->r_hist);
+        for (int j = 0; j < kITaps - 1; ++j) { sm.rs[j][lane] = rh[j]; }
+    }
+
+    // ---- role-private state
+    float g = 0.f, fph = 0.f, ffr = 0.f, yr = 0.f, yi = 0.f;
+    float2 cur[T], nxt[T];
+    const float2* __restrict__ in = p.iq + (long long)ch * p.in_stride;
+    LoopConsts lc = {};
+    if (role == kRLoop) {
+        g = sp->agc_gain; fph = sp->fll_phase; ffr = sp->fll_freq;
+#pragma unroll
+        for (int i = 0; i < T; ++i) { cur[i] = (i < count) ? __ldg(in + i) : make_float2(0.f, 0.f); }
+        lc = load_loop_consts(p);
+        yr = mul_rn(cur[0].x, g); yi = mul_rn(cur[0].y, g);
+    }
+    SymConsts kc = {};
+    float mu = 0.f, om = 0.f;
+    int offset = 0, nsym_t = 0;
+    if (role == kRTiming) {
+        mu = sp->tr_mu; om = sp->tr_omega; offset = sp->tr_offset;
+        kc = load_sym_consts(p);
+    }
+    float cph = 0.f, cfr = 0.f, ph2 = 0.f;
+    int nsym_c = 0;
+    if (role == kRCostas) {
+        cph = sp->costas_phase; cfr = sp->costas_freq; ph2 = sp->costas_ph2;
+        kc = load_sym_consts(p);
+    }
+    SlicerState sl = {};
+    float err_blocks[TDM_SYNC_BLOCKS];
+    const long long out_base = (long long)ch * p.out_stride;
+    if (role == kRSlicer) {
+        sl.prev = sp->prev_sym; sl.err_ptr = sp->err_ptr; sl.err_disp = sp->err_disp;
+        sl.err_partial = sp->err_partial; sl.standarderr = sp->standarderr; sl.sync = sp->sync;
+        sl.nsym = 0;
+#pragma unroll
+        for (int j = 0; j < TDM_SYNC_BLOCKS; ++j) { err_blocks[j] = sp->err_blocks[j]; }
+    }
+    __syncthreads();
+
+#ifdef TDM_ROLE_TIMING
+    long long work_cycles = 0;
+    const long long t_begin = clock64();
+#endif
+#pragma unroll 1
+    for (int t = -1; t <= nblk + 3; ++t) {
+#ifdef TDM_ROLE_TIMING
+        const long long c0 = clock64();
+#endif
+        if (role == kRLoop) {
+            // ================= LOOP: block b = t =================
+            if (t >= 0 && t < nblk) {
+                const int n0 = t * T;
+                const int valid = min(T, count - n0);
+#pragma unroll
+                for (int i = 0; i < T; ++i) {
+                    const int n = n0 + T + i;
+                    nxt[i] = (n < count) ? __ldg(in + n) : make_float2(0.f, 0.f);
+                }
+                if (n0 + 5 * T < count) { asm volatile("prefetch.global.L2 [%0];" :: "l"(in + n0 + 5 * T)); }
+                // chains of this block's outputs: far part from the P/Q warps ...
+                float2 accP[T], accQ[T];
+#pragma unroll
+                for (int i = 0; i < T; ++i) { accP[i] = sm.pfar[t & 1][i][lane]; accQ[i] = sm.qfar[t & 1][i][lane]; }
+                const int mslot = (t + 7) & (kWsXSlots - 1);     // ring block of sample block t-1
+                const int xslot = (t + 8) & (kWsXSlots - 1);
+                if (valid == T) {
+                    // ... then the previous block's 8 samples (sample j meets output i at tap 56 + j - i) and the
+                    // block's own (sample i meets output q >= i at tap 64 + i - q), all in ONE basic block so the
+                    // scheduler can sink the 128 previous-block FFMA2 into the recurrence's latency shadow
+                    {
+                        float2 h[T];
+#pragma unroll
+                        for (int j = 0; j < T; ++j) { h[j] = sm.xs[mslot * T + j][lane]; }
+#pragma unroll
+                        for (int j = 0; j < T; ++j) {
+#pragma unroll
+                            for (int i = 0; i < T; ++i) {
+                                accP[i] = fma2_rn(p.be_a[kHist - T + j - i], h[j], accP[i]);
+                                accQ[i] = fma2_rn(p.be_b[kHist - T + j - i], h[j], accQ[i]);
+                            }
+                        }
+                    }
+#pragma unroll
+                    for (int i = 0; i < T; ++i) {
+                        float sn, cs;
+                        sincos_canon(fph, sn, cs);
+                        const float2 x = make_float2(fma_rn(yr, cs, mul_rn(yi, sn)), fma_rn(yi, cs, -mul_rn(yr, sn)));
+                        sm.xs[xslot * T + i][lane] = x;
+#pragma unroll
+                        for (int q = i; q < T; ++q) {
+                            accP[q] = fma2_rn(p.be_a[kHist + i - q], x, accP[q]);
+                            accQ[q] = fma2_rn(p.be_b[kHist + i - q], x, accQ[q]);
+                        }
+                        fll_update(lc, accP[i].x, accP[i].y, accQ[i].x, accQ[i].y, fph, ffr);
+                        // AGC recurrence, one sample ahead: gain after this sample, then the next sample's product
+                        const float amp = sqrt_rn_nobranch(fma_rn(yr, yr, mul_rn(yi, yi)));
+                        g = fma_rn(sub_rn(lc.agc_set, amp), lc.agc_rate, g);
+                        g = g > lc.agc_max ? lc.agc_max : g;
+                        const float2 nx = (i + 1 < T) ? cur[(i + 1) & (T - 1)] : nxt[0];
+                        yr = mul_rn(nx.x, g); yi = mul_rn(nx.y, g);
+                    }
+                } else {
+                    // partial last block of a call: compact rolled code (previous block one sample per trip, then the
+                    // shift-register form in which position q always meets tap 64 - q)
+#pragma unroll 1
+                    for (int j = 0; j < T; ++j) {
+                        const float2 h = sm.xs[mslot * T + j][lane];
+#pragma unroll
+                        for (int i = 0; i < T; ++i) {
+                            accP[i] = fma2_rn(p.be_a[kHist - T + j - i], h, accP[i]);
+                            accQ[i] = fma2_rn(p.be_b[kHist - T + j - i], h, accQ[i]);
+                        }
+                    }
+#pragma unroll 1
+                    for (int i = 0; i < valid; ++i) {
+                        float sn, cs;
+                        sincos_canon(fph, sn, cs);
+                        const float2 x = make_float2(fma_rn(yr, cs, mul_rn(yi, sn)), fma_rn(yi, cs, -mul_rn(yr, sn)));
+                        sm.xs[xslot * T + i][lane] = x;
+#pragma unroll
+                        for (int q = 0; q < T; ++q) {
+                            accP[q] = fma2_rn(p.be_a[kHist - q], x, accP[q]);
+                            accQ[q] = fma2_rn(p.be_b[kHist - q], x, accQ[q]);
+                        }
+                        fll_update(lc, accP[0].x, accP[0].y, accQ[0].x, accQ[0].y, fph, ffr);
+                        const float amp = sqrt_rn_nobranch(fma_rn(yr, yr, mul_rn(yi, yi)));
+                        g = fma_rn(sub_rn(lc.agc_set, amp), lc.agc_rate, g);
+                        g = g > lc.agc_max ? lc.agc_max : g;
+#pragma unroll
+                        for (int q = 0; q < T - 1; ++q) { accP[q] = accP[q + 1]; accQ[q] = accQ[q + 1]; cur[q] = cur[q + 1]; }
+                        yr = mul_rn(cur[0].x, g); yi = mul_rn(cur[0].y, g);
+                    }
+                }
+#pragma unroll
+                for (int i = 0; i < T; ++i) { cur[i] = nxt[i]; }
+            }
+        } else if (role == kRPfar || role == kRQfar) {
+            // ================= P-far / Q-far: block b = t + 1 =================
+            const int b = t + 1;
+            if (b < nblk) {
+                float2 acc[T];
+#pragma unroll
+                for (int i = 0; i < T; ++i) { acc[i] = make_float2(0.f, 0.f); }
+                ws3_fir_blocks<kWsFar, T>(p, sm.xs, lane, b, role == kRPfar ? 0 : 1, 0, acc);
+                float2 (*dst)[32] = (role == kRPfar) ? sm.pfar[b & 1] : sm.qfar[b & 1];
+#pragma unroll
+                for (int i = 0; i < T; ++i) { dst[i][lane] = acc[i]; }
+            }
+        } else if (role == kRRrcA || role == kRRrcB) {
+            // ================= RRC: block b = t - 1, outputs 0..3 (A) or 4..7 (B) =================
+            const int b = t - 1;
+            if (b >= 0 && b < nblk) {
+                float2 acc[T / 2];
+#pragma unroll
+                for (int i = 0; i < T / 2; ++i) { acc[i] = make_float2(0.f, 0.f); }
+                const int i0 = (role == kRRrcA) ? 0 : T / 2;
+                ws3_fir_blocks<kWsFar + 2, T / 2>(p, sm.xs, lane, b, 2, T / 2 - i0, acc);
+#pragma unroll
+                for (int i = 0; i < T / 2; ++i) {
+                    sm.rs[(kITaps - 1 + b * T + i0 + i) & (kWsREntries - 1)][lane] = acc[i];
+                }
+            }
+        } else if (role == kRTiming) {
+            // ================= TIMING: symbols whose newest input sample lies in block t - 2 =================
+            if (t >= 2) {
+                const int lim = min(count, (t - 1) * T);
+                while (offset < lim) {
+                    const float2 y = timing_step2<kWsREntries>(kc, sm.bank, &sm.rs[0][0], lane, mu, om, offset);
+                    sm.ys[nsym_t & (kSymRing - 1)][lane] = y;
+                    ++nsym_t;
+                }
+                sm.ycount[t & 1][lane] = nsym_t;
+            }
+        } else if (role == kRCostas) {
+            // ================= COSTAS: the symbols TIMING finished during tick t - 1 =================
+            if (t >= 3) {
+                const int target = sm.ycount[(t - 1) & 1][lane];
+                while (nsym_c < target) {
+                    const float2 y = sm.ys[nsym_c & (kSymRing - 1)][lane];
+                    sm.us[nsym_c & (kSymRing - 1)][lane] = costas_loop_step(kc, y, cph, cfr, ph2);
+                    ++nsym_c;
+                }
+                sm.ucount[t & 1][lane] = nsym_c;
+            }
+        } else {
+            // ================= SLICER: the symbols COSTAS finished during tick t - 1 =================
+            if (t >= 4) {
+                const int target = sm.ucount[(t - 1) & 1][lane];
+                do {    // one trip; more only if a tick ever carried over 5 symbols
+                    slicer_symbols<5, kSymRing>(p, sm.us, lane, min(target - sl.nsym, 5), sl, err_blocks, active, out_base);
+                } while (__any_sync(0xffffffffu, sl.nsym < target));
+            }
+        }
+#ifdef TDM_ROLE_TIMING
+        work_cycles += clock64() - c0;
+#endif
+        __syncthreads();
+    }
+#ifdef TDM_ROLE_TIMING
+    if (blockIdx.x == 3 && lane == 0) {
+        unsigned wid, smid;
+        asm volatile("mov.u32 %0, %%warpid;" : "=r"(wid));
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        printf("ws3 role %d (hw warp slot %u on SM %u): work %lld of %lld cycles (%.1f%%), per tick %lld\n", role, wid, smid, work_cycles,
+               clock64() - t_begin, 100.0 * work_cycles / (double)(clock64() - t_begin), work_cycles / (nblk + 4));
+    }
+#endif
+
+    // ---- carry state out
+    if (!active) { return; }
+    if (role == kRLoop) {
+        sp->agc_gain = g; sp->fll_phase = fph; sp->fll_freq = ffr;
+        sp->n_samples += (unsigned long long)count;
+    } else if (role == kRPfar) {
+        float2* xh = reinterpret_cast<float2*>(sp->x_hist);
+        for (int m = 0; m < kHist; ++m) {
+            const long long q = (long long)count + m;
+            xh[m] = sm.xs[(int)((q / T) & (kWsXSlots - 1)) * T + (int)(q % T)][lane];
+        }
+    } else if (role == kRRrcA) {
+        float2* rh = reinterpret_cast<float2*>(sp->r_hist);
+        for (int j = 0; j < kITaps - 1; ++j) { rh[j] = sm.rs[(count + j) & (kWsREntries - 1)][lane]; }
+    } else if (role == kRTiming) {
+        sp->tr_mu = mu; sp->tr_omega = om; sp->tr_offset = offset - count;
+    } else if (role == kRCostas) {
+        sp->costas_phase = cph; sp->costas_freq = cfr; sp->costas_ph2 = ph2;
+    } else if (role == kRSlicer) {
+        sp->prev_sym = sl.prev; sp->err_ptr = sl.err_ptr; sp->err_disp = sl.err_disp;
+        sp->err_partial = sl.err_partial; sp->standarderr = sl.standarderr; sp->sync = sl.sync;
+        sp->n_symbols += (unsigned long long)sl.nsym;
+#pragma unroll
+        for (int j = 0; j < TDM_SYNC_BLOCKS; ++j) { sp->err_blocks[j] = err_blocks[j]; }
+        p.out_counts[ch] = sl.nsym;
+    }
+}
+
+int launch_ws3(const DemodParams& p_in, cudaStream_t stream, int placement) {
+    DemodParams p = p_in;
+    const float* src[3] = { p.be_a, p.be_b, p.rrc };
+    for (int f = 0; f < 3; ++f) {
+        for (int j = 0; j < kTapPad; ++j) {
+            const int k = j - (kWsT - 1);
+            p.tpad[f][j] = (k >= 0 && k < kTaps) ? src[f][k] : 0.f;
+        }
+    }
+    const int grid = (p.n_channels + 31) / 32;
+    auto go = [&](auto kern) {
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Ws3Smem));
+        kern<<<grid, 256, sizeof(Ws3Smem), stream>>>(p);
+    };
+    if (placement == 1) { go(demod_ws3_kernel<1>); }
+    else if (placement == 2) { go(demod_ws3_kernel<2>); }
+    else { go(demod_ws3_kernel<0>); }
+    return cudaGetLastError() == cudaSuccess ? 1 : -1;
+}
+
+// ---------------------------------------------------------------------------------------
 // dibit packing for the multi-GPU gather: 4 symbols per byte, first symbol in bits 7..6.
 // ---------------------------------------------------------------------------------------
 __global__ void pack_dibits_kernel(const uint8_t* __restrict__ dibits, long long in_stride,
@@ -1048,6 +1538,9 @@ const char* demod_variant_name(int variant) {
         case 4: return "ws8";
         case 5: return "ws8b";
         case 6: return "ws8b-8w";
+        case 7: return "ws3";
+        case 8: return "ws3-p1";
+        case 9: return "ws3-p2";
         default: return "auto";
     }
 }
@@ -1065,6 +1558,9 @@ int launch_demod(const DemodParams& p, int variant, cudaStream_t stream) {
         case 4: return launch_ws(p, stream);
         case 5: return launch_ws2(p, stream, 6);
         case 6: return launch_ws2(p, stream, 8);
+        case 7: return launch_ws3(p, stream, 0);
+        case 8: return launch_ws3(p, stream, 1);
+        case 9: return launch_ws3(p, stream, 2);
         default: return -1;
     }
 }
