@@ -1035,18 +1035,25 @@ int launch_ws2(const DemodParams& p_in, cudaStream_t stream, int warps) {
 // Chains and their term order are unchanged (far -> previous block -> own block, ascending taps),
 // so the results are bit-identical to every other variant and to the canonical-order checker.
 // ---------------------------------------------------------------------------------------
-enum Ws3Role { kRLoop = 0, kRPfar = 1, kRQfar = 2, kRRrcA = 3, kRRrcB = 4, kRTiming = 5, kRCostas = 6, kRSlicer = 7 };
+enum Ws3Role { kRLoop = 0, kRPfar = 1, kRQfar = 2, kRRrcA = 3, kRRrcB = 4, kRTiming = 5, kRCostas = 6, kRSlicer = 7, kRIdle = 8, kRAgc = 9 };
 
-// warp -> role.  Warps w and w+4 share a scheduler (SMSP = warp slot mod 4 up to a rotation).
+// warp -> role.  Warps w, w+4, w+8 share a scheduler (SMSP = warp slot mod 4 up to a rotation).
+template <int PLACEMENT>
+struct Ws3Placement {
+    static constexpr unsigned long long r0 = kRLoop, rP = kRPfar, rQ = kRQfar, rA = kRRrcA, rB = kRRrcB, rT = kRTiming, rC = kRCostas,
+                                        rS = kRSlicer, rI = kRIdle, rG = kRAgc;
+    // one role per nibble, warp 0 in the lowest (a table indexed by the warp number would live in local memory).
+    // 12 warps; columns = schedulers:        SMSP a     SMSP b     SMSP c     SMSP d
+    static constexpr unsigned long long tab =
+        PLACEMENT == 0 ? (r0 | rT << 4 | rP << 8 | rQ << 12 |  rG << 16 | rC << 20 | rA << 24 | rB << 28 |  rI << 32 | rS << 36 | rI << 40 | rI << 44)
+      : PLACEMENT == 1 ? (r0 | rT << 4 | rP << 8 | rQ << 12 |  rI << 16 | rI << 20 | rA << 24 | rB << 28 |  rI << 32 | rG << 36 | rC << 40 | rS << 44)
+      : PLACEMENT == 2 ? (r0 | rT << 4 | rP << 8 | rQ << 12 |  rS << 16 | rG << 20 | rA << 24 | rB << 28 |  rI << 32 | rC << 36 | rI << 40 | rI << 44)
+      :                  (r0 | rP << 4 | rQ << 8 | rA << 12 |  rG << 16 | rT << 20 | rC << 24 | rB << 28 |  rI << 32 | rS << 36 | rI << 40 | rI << 44);
+    static constexpr int warps = 12;
+};
 template <int PLACEMENT>
 __device__ __forceinline__ int ws3_role_of_warp(int warp) {
-    // one role per nibble, warp 0 in the lowest (a table indexed by the warp number would live in local memory)
-    constexpr unsigned r0 = kRLoop, rP = kRPfar, rQ = kRQfar, rA = kRRrcA, rB = kRRrcB, rT = kRTiming, rC = kRCostas, rS = kRSlicer;
-    constexpr unsigned tab =
-        PLACEMENT == 0 ? (r0 | rP << 4 | rQ << 8 | rA << 12 | rS << 16 | rT << 20 | rC << 24 | rB << 28)    // LOOP+SLICER; P+TIMING; Q+COSTAS; RRC A+B
-      : PLACEMENT == 1 ? (r0 | rP << 4 | rQ << 8 | rA << 12 | rB << 16 | rT << 20 | rC << 24 | rS << 28)    // LOOP+RRC-B; P+TIMING; Q+COSTAS; RRC-A+SLICER
-      :                  (r0 | rP << 4 | rQ << 8 | rA << 12 | rC << 16 | rB << 20 | rT << 24 | rS << 28);   // LOOP+COSTAS; P+RRC-B; Q+TIMING; RRC-A+SLICER
-    return (int)((tab >> (4 * warp)) & 0xfu);
+    return (int)((Ws3Placement<PLACEMENT>::tab >> (4 * warp)) & 0xfull);
 }
 
 // (re, im) chains of one real-tap filter for NI consecutive outputs of a block, over NB x-ring blocks
@@ -1088,17 +1095,21 @@ __device__ __forceinline__ void ws3_fir_blocks(const DemodParams& p, const float
 }
 
 // timing_step with the three interpolator chains advanced pairwise by FFMA2 (same terms, same order).
+// The polyphase bank is read from a per-lane replica, bank4[(phase * 2 + half) * 32 + lane] (float4): lanes
+// sit on different phases, and rows of the plain 128 x 8 table collide 8 ways on shared-memory banks, which
+// put ~100 cycles of LSU time per symbol on this recurrence; in the replica every quarter-warp access is
+// conflict free whatever the phases are.
 template <int RE>
-__device__ __forceinline__ float2 timing_step2(const SymConsts& kc, const float* __restrict__ bank_s,
+__device__ __forceinline__ float2 timing_step2(const SymConsts& kc, const float4* __restrict__ bank4,
                                                const float2* rs, int lane, float& mu, float& om, int& offset) {
-    const float phf = fminf(fmaxf(floorf(mul_rn(mu, (float)kIPhases)), 0.0f), (float)(kIPhases - 1));   // see timing_step
-    const int ph = (int)phf;
+    // phase = clamp(floor(mu*128), 0, 127) (complex_fd.cpp:101); clamped as a float first (see timing_step),
+    // then ONE conversion: floor commutes with a clamp to integer bounds
+    const int ph = __float2int_rd(fminf(fmaxf(mul_rn(mu, (float)kIPhases), 0.0f), (float)(kIPhases - 1)));
     const int plo = max(ph - 1, 0);
     const int phi = min(ph + 1, kIPhases - 1);
-    const float4* r0 = reinterpret_cast<const float4*>(bank_s + ph * kITaps);
-    const float4* r1 = reinterpret_cast<const float4*>(bank_s + phi * kITaps);
-    const float4* r2 = reinterpret_cast<const float4*>(bank_s + plo * kITaps);
-    const float4 t0a = r0[0], t0b = r0[1], t1a = r1[0], t1b = r1[1], t2a = r2[0], t2b = r2[1];
+    const float4 t0a = bank4[(ph * 2) * 32 + lane], t0b = bank4[(ph * 2 + 1) * 32 + lane];
+    const float4 t1a = bank4[(phi * 2) * 32 + lane], t1b = bank4[(phi * 2 + 1) * 32 + lane];
+    const float4 t2a = bank4[(plo * 2) * 32 + lane], t2b = bank4[(plo * 2 + 1) * 32 + lane];
     const float t0[8] = { t0a.x, t0a.y, t0a.z, t0a.w, t0b.x, t0b.y, t0b.z, t0b.w };
     const float t1[8] = { t1a.x, t1a.y, t1a.z, t1a.w, t1b.x, t1b.y, t1b.z, t1b.w };
     const float t2[8] = { t2a.x, t2a.y, t2a.z, t2a.w, t2b.x, t2b.y, t2b.z, t2b.w };
@@ -1207,26 +1218,36 @@ __device__ __forceinline__ void slicer_symbols(const DemodParams& p, const float
 
 constexpr int kSymRing = 16;      // >= symbols in flight between two symbol-rate roles (<= 5 per tick, two ticks)
 struct Ws3Smem {
-    float bank[kIPhases * kITaps];
+    float4 bank4[kIPhases * 2][32];   // per-lane replica of the 128 x 8 interpolator bank (see timing_step2)
     float2 xs[kWsXEntries][32];
     float2 rs[kWsREntries][32];
     float2 pfar[2][kWsT][32];
     float2 qfar[2][kWsT][32];
+    float2 ysc[2][kWsT][32];       // AGC -> LOOP: gain-scaled input samples of a block
     float2 ys[kSymRing][32];       // TIMING -> COSTAS: interpolated symbols
     float2 us[kSymRing][32];       // COSTAS -> SLICER: carrier-corrected symbols
     int ycount[2][32];
     int ucount[2][32];
 };
 
+// All warps of the CTA meet here once per tick.  Spelled as the PTX barrier because every role runs its
+// OWN tick loop (no per-tick role dispatch, no registers of other roles live): the warps arrive at barrier 0
+// from different program counters, whole warps at a time, the same number of times (ws3_ticks()).
+__device__ __forceinline__ void ws3_tick_barrier() { asm volatile("bar.sync 0;" ::: "memory"); }
+__device__ __forceinline__ int ws3_last_tick(int nblk) { return nblk + 3; }   // ticks run t = -1 .. nblk + 3
+
 template <int PLACEMENT>
-__global__ void __launch_bounds__(256) demod_ws3_kernel(const __grid_constant__ DemodParams p) {
+__global__ void __launch_bounds__(Ws3Placement<PLACEMENT>::warps * 32) demod_ws3_kernel(const __grid_constant__ DemodParams p) {
     constexpr int T = kWsT;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     Ws3Smem& sm = *reinterpret_cast<Ws3Smem*>(smem_raw);
     const int lane = threadIdx.x & 31;
     const int role = ws3_role_of_warp<PLACEMENT>(threadIdx.x >> 5);
 
-    for (int i = threadIdx.x; i < kIPhases * kITaps; i += blockDim.x) { sm.bank[i] = p.bank[i]; }
+    {
+        const float4* __restrict__ b4 = reinterpret_cast<const float4*>(p.bank);
+        for (int i = threadIdx.x; i < kIPhases * 2 * 32; i += blockDim.x) { sm.bank4[i / 32][i % 32] = __ldg(b4 + i / 32); }
+    }
     for (int i = threadIdx.x; i < (kWsXEntries - kHist) * 32; i += blockDim.x) {
         sm.xs[kHist + i / 32][i % 32] = make_float2(0.f, 0.f);     // see demod_ws_kernel: zero taps must meet finite data
     }
@@ -1242,6 +1263,7 @@ __global__ void __launch_bounds__(256) demod_ws3_kernel(const __grid_constant__ 
     tdm_channel_state* __restrict__ sp = p.states + ch;
     const int count = p.count;
     const int nblk = (count + T - 1) / T;
+    const int t_last = ws3_last_tick(nblk);
     if (role == kRPfar) {
         const float2* xh = reinterpret_cast<const float2*>(sp->x_hist);
         for (int m = 0; m < kHist; ++m) { sm.xs[m][lane] = xh[m]; }
@@ -1250,57 +1272,23 @@ __global__ void __launch_bounds__(256) demod_ws3_kernel(const __grid_constant__ 
         const float2* rh = reinterpret_cast<const float2*>(sp->r_hist);
         for (int j = 0; j < kITaps - 1; ++j) { sm.rs[j][lane] = rh[j]; }
     }
-
-    // ---- role-private state
-    float g = 0.f, fph = 0.f, ffr = 0.f, yr = 0.f, yi = 0.f;
-    float2 cur[T], nxt[T];
-    const float2* __restrict__ in = p.iq + (long long)ch * p.in_stride;
-    LoopConsts lc = {};
-    if (role == kRLoop) {
-        g = sp->agc_gain; fph = sp->fll_phase; ffr = sp->fll_freq;
-#pragma unroll
-        for (int i = 0; i < T; ++i) { cur[i] = (i < count) ? __ldg(in + i) : make_float2(0.f, 0.f); }
-        lc = load_loop_consts(p);
-        yr = mul_rn(cur[0].x, g); yi = mul_rn(cur[0].y, g);
-    }
-    SymConsts kc = {};
-    float mu = 0.f, om = 0.f;
-    int offset = 0, nsym_t = 0;
-    if (role == kRTiming) {
-        mu = sp->tr_mu; om = sp->tr_omega; offset = sp->tr_offset;
-        kc = load_sym_consts(p);
-    }
-    float cph = 0.f, cfr = 0.f, ph2 = 0.f;
-    int nsym_c = 0;
-    if (role == kRCostas) {
-        cph = sp->costas_phase; cfr = sp->costas_freq; ph2 = sp->costas_ph2;
-        kc = load_sym_consts(p);
-    }
-    SlicerState sl = {};
-    float err_blocks[TDM_SYNC_BLOCKS];
-    const long long out_base = (long long)ch * p.out_stride;
-    if (role == kRSlicer) {
-        sl.prev = sp->prev_sym; sl.err_ptr = sp->err_ptr; sl.err_disp = sp->err_disp;
-        sl.err_partial = sp->err_partial; sl.standarderr = sp->standarderr; sl.sync = sp->sync;
-        sl.nsym = 0;
-#pragma unroll
-        for (int j = 0; j < TDM_SYNC_BLOCKS; ++j) { err_blocks[j] = sp->err_blocks[j]; }
-    }
     __syncthreads();
 
-#ifdef TDM_ROLE_TIMING
-    long long work_cycles = 0;
-    const long long t_begin = clock64();
-#endif
+    if (role == kRAgc) {
+        // ================= AGC: FastAGC recurrence [A.3], block b = t + 1 (one tick ahead of LOOP) =================
+        // The gain loop does not depend on anything downstream, so it runs as its own role: LOOP then carries
+        // only the FLL recurrence (no sqrt chain, no global loads, ~25 % fewer instructions per sample).
+        float g = sp->agc_gain;
+        const float2* __restrict__ in = p.iq + (long long)ch * p.in_stride;
+        const LoopConsts lc = load_loop_consts(p);
+        float2 cur[T], nxt[T];
+#pragma unroll
+        for (int i = 0; i < T; ++i) { cur[i] = (i < count) ? __ldg(in + i) : make_float2(0.f, 0.f); }
 #pragma unroll 1
-    for (int t = -1; t <= nblk + 3; ++t) {
-#ifdef TDM_ROLE_TIMING
-        const long long c0 = clock64();
-#endif
-        if (role == kRLoop) {
-            // ================= LOOP: block b = t =================
-            if (t >= 0 && t < nblk) {
-                const int n0 = t * T;
+        for (int t = -1; t <= t_last; ++t) {
+            const int b = t + 1;
+            if (b < nblk) {
+                const int n0 = b * T;
                 const int valid = min(T, count - n0);
 #pragma unroll
                 for (int i = 0; i < T; ++i) {
@@ -1308,6 +1296,36 @@ __global__ void __launch_bounds__(256) demod_ws3_kernel(const __grid_constant__ 
                     nxt[i] = (n < count) ? __ldg(in + n) : make_float2(0.f, 0.f);
                 }
                 if (n0 + 5 * T < count) { asm volatile("prefetch.global.L2 [%0];" :: "l"(in + n0 + 5 * T)); }
+#pragma unroll
+                for (int i = 0; i < T; ++i) {
+                    const float yr = mul_rn(cur[i].x, g), yi = mul_rn(cur[i].y, g);
+                    sm.ysc[b & 1][i][lane] = make_float2(yr, yi);
+                    const float amp = sqrt_rn_nobranch(fma_rn(yr, yr, mul_rn(yi, yi)));
+                    float gn = fma_rn(sub_rn(lc.agc_set, amp), lc.agc_rate, g);
+                    gn = gn > lc.agc_max ? lc.agc_max : gn;
+                    g = (i < valid) ? gn : g;            // samples past the end of the call do not exist
+                }
+#pragma unroll
+                for (int i = 0; i < T; ++i) { cur[i] = nxt[i]; }
+            }
+            ws3_tick_barrier();
+        }
+        if (active) {
+            sp->agc_gain = g;
+            sp->n_samples += (unsigned long long)count;
+        }
+    } else if (role == kRLoop) {
+        // ================= LOOP: FLL recurrence on the gain-scaled samples, block b = t =================
+        float fph = sp->fll_phase, ffr = sp->fll_freq;
+        const LoopConsts lc = load_loop_consts(p);
+        ws3_tick_barrier();                                  // tick t = -1
+#pragma unroll 1
+        for (int t = 0; t <= t_last; ++t) {
+            if (t < nblk) {
+                const int valid = min(T, count - t * T);
+                float2 ysc[T];
+#pragma unroll
+                for (int i = 0; i < T; ++i) { ysc[i] = sm.ysc[t & 1][i][lane]; }
                 // chains of this block's outputs: far part from the P/Q warps ...
                 float2 accP[T], accQ[T];
 #pragma unroll
@@ -1335,6 +1353,7 @@ __global__ void __launch_bounds__(256) demod_ws3_kernel(const __grid_constant__ 
                     for (int i = 0; i < T; ++i) {
                         float sn, cs;
                         sincos_canon(fph, sn, cs);
+                        const float yr = ysc[i].x, yi = ysc[i].y;
                         const float2 x = make_float2(fma_rn(yr, cs, mul_rn(yi, sn)), fma_rn(yi, cs, -mul_rn(yr, sn)));
                         sm.xs[xslot * T + i][lane] = x;
 #pragma unroll
@@ -1343,12 +1362,6 @@ __global__ void __launch_bounds__(256) demod_ws3_kernel(const __grid_constant__ 
                             accQ[q] = fma2_rn(p.be_b[kHist + i - q], x, accQ[q]);
                         }
                         fll_update(lc, accP[i].x, accP[i].y, accQ[i].x, accQ[i].y, fph, ffr);
-                        // AGC recurrence, one sample ahead: gain after this sample, then the next sample's product
-                        const float amp = sqrt_rn_nobranch(fma_rn(yr, yr, mul_rn(yi, yi)));
-                        g = fma_rn(sub_rn(lc.agc_set, amp), lc.agc_rate, g);
-                        g = g > lc.agc_max ? lc.agc_max : g;
-                        const float2 nx = (i + 1 < T) ? cur[(i + 1) & (T - 1)] : nxt[0];
-                        yr = mul_rn(nx.x, g); yi = mul_rn(nx.y, g);
                     }
                 } else {
                     // partial last block of a call: compact rolled code (previous block one sample per trip, then the
@@ -1366,6 +1379,7 @@ __global__ void __launch_bounds__(256) demod_ws3_kernel(const __grid_constant__ 
                     for (int i = 0; i < valid; ++i) {
                         float sn, cs;
                         sincos_canon(fph, sn, cs);
+                        const float yr = ysc[0].x, yi = ysc[0].y;
                         const float2 x = make_float2(fma_rn(yr, cs, mul_rn(yi, sn)), fma_rn(yi, cs, -mul_rn(yr, sn)));
                         sm.xs[xslot * T + i][lane] = x;
 #pragma unroll
@@ -1374,56 +1388,86 @@ __global__ void __launch_bounds__(256) demod_ws3_kernel(const __grid_constant__ 
                             accQ[q] = fma2_rn(p.be_b[kHist - q], x, accQ[q]);
                         }
                         fll_update(lc, accP[0].x, accP[0].y, accQ[0].x, accQ[0].y, fph, ffr);
-                        const float amp = sqrt_rn_nobranch(fma_rn(yr, yr, mul_rn(yi, yi)));
-                        g = fma_rn(sub_rn(lc.agc_set, amp), lc.agc_rate, g);
-                        g = g > lc.agc_max ? lc.agc_max : g;
 #pragma unroll
-                        for (int q = 0; q < T - 1; ++q) { accP[q] = accP[q + 1]; accQ[q] = accQ[q + 1]; cur[q] = cur[q + 1]; }
-                        yr = mul_rn(cur[0].x, g); yi = mul_rn(cur[0].y, g);
+                        for (int q = 0; q < T - 1; ++q) { accP[q] = accP[q + 1]; accQ[q] = accQ[q + 1]; ysc[q] = ysc[q + 1]; }
                     }
                 }
-#pragma unroll
-                for (int i = 0; i < T; ++i) { cur[i] = nxt[i]; }
             }
-        } else if (role == kRPfar || role == kRQfar) {
-            // ================= P-far / Q-far: block b = t + 1 =================
+            ws3_tick_barrier();
+        }
+        if (active) { sp->fll_phase = fph; sp->fll_freq = ffr; }
+    } else if (role == kRPfar || role == kRQfar) {
+        // ================= P-far / Q-far: the oldest 56 - i terms of block b = t + 1 =================
+        const int f = (role == kRPfar) ? 0 : 1;
+        float2 (*const dst)[T][32] = (role == kRPfar) ? sm.pfar : sm.qfar;
+#pragma unroll 1
+        for (int t = -1; t <= t_last; ++t) {
             const int b = t + 1;
             if (b < nblk) {
                 float2 acc[T];
 #pragma unroll
                 for (int i = 0; i < T; ++i) { acc[i] = make_float2(0.f, 0.f); }
-                ws3_fir_blocks<kWsFar, T>(p, sm.xs, lane, b, role == kRPfar ? 0 : 1, 0, acc);
-                float2 (*dst)[32] = (role == kRPfar) ? sm.pfar[b & 1] : sm.qfar[b & 1];
+                ws3_fir_blocks<kWsFar, T>(p, sm.xs, lane, b, f, 0, acc);
 #pragma unroll
-                for (int i = 0; i < T; ++i) { dst[i][lane] = acc[i]; }
+                for (int i = 0; i < T; ++i) { dst[b & 1][i][lane] = acc[i]; }
             }
-        } else if (role == kRRrcA || role == kRRrcB) {
-            // ================= RRC: block b = t - 1, outputs 0..3 (A) or 4..7 (B) =================
+            ws3_tick_barrier();
+        }
+        if (active && role == kRPfar) {
+            float2* xh = reinterpret_cast<float2*>(sp->x_hist);
+            for (int m = 0; m < kHist; ++m) {
+                const long long q = (long long)count + m;
+                xh[m] = sm.xs[(int)((q / T) & (kWsXSlots - 1)) * T + (int)(q % T)][lane];
+            }
+        }
+    } else if (role == kRRrcA || role == kRRrcB) {
+        // ================= RRC: block b = t - 1, outputs 0..3 (A) or 4..7 (B), all 65 taps =================
+        const int i0 = (role == kRRrcA) ? 0 : T / 2;
+#pragma unroll 1
+        for (int t = -1; t <= t_last; ++t) {
             const int b = t - 1;
             if (b >= 0 && b < nblk) {
                 float2 acc[T / 2];
 #pragma unroll
                 for (int i = 0; i < T / 2; ++i) { acc[i] = make_float2(0.f, 0.f); }
-                const int i0 = (role == kRRrcA) ? 0 : T / 2;
                 ws3_fir_blocks<kWsFar + 2, T / 2>(p, sm.xs, lane, b, 2, T / 2 - i0, acc);
 #pragma unroll
                 for (int i = 0; i < T / 2; ++i) {
                     sm.rs[(kITaps - 1 + b * T + i0 + i) & (kWsREntries - 1)][lane] = acc[i];
                 }
             }
-        } else if (role == kRTiming) {
-            // ================= TIMING: symbols whose newest input sample lies in block t - 2 =================
+            ws3_tick_barrier();
+        }
+        if (active && role == kRRrcA) {
+            float2* rh = reinterpret_cast<float2*>(sp->r_hist);
+            for (int j = 0; j < kITaps - 1; ++j) { rh[j] = sm.rs[(count + j) & (kWsREntries - 1)][lane]; }
+        }
+    } else if (role == kRTiming) {
+        // ================= TIMING: symbols whose newest input sample lies in block t - 2 =================
+        float mu = sp->tr_mu, om = sp->tr_omega;
+        int offset = sp->tr_offset, nsym_t = 0;
+        const SymConsts kc = load_sym_consts(p);
+#pragma unroll 1
+        for (int t = -1; t <= t_last; ++t) {
             if (t >= 2) {
                 const int lim = min(count, (t - 1) * T);
                 while (offset < lim) {
-                    const float2 y = timing_step2<kWsREntries>(kc, sm.bank, &sm.rs[0][0], lane, mu, om, offset);
+                    const float2 y = timing_step2<kWsREntries>(kc, &sm.bank4[0][0], &sm.rs[0][0], lane, mu, om, offset);
                     sm.ys[nsym_t & (kSymRing - 1)][lane] = y;
                     ++nsym_t;
                 }
                 sm.ycount[t & 1][lane] = nsym_t;
             }
-        } else if (role == kRCostas) {
-            // ================= COSTAS: the symbols TIMING finished during tick t - 1 =================
+            ws3_tick_barrier();
+        }
+        if (active) { sp->tr_mu = mu; sp->tr_omega = om; sp->tr_offset = offset - count; }
+    } else if (role == kRCostas) {
+        // ================= COSTAS: the symbols TIMING finished during tick t - 1 =================
+        float cph = sp->costas_phase, cfr = sp->costas_freq, ph2 = sp->costas_ph2;
+        int nsym_c = 0;
+        const SymConsts kc = load_sym_consts(p);
+#pragma unroll 1
+        for (int t = -1; t <= t_last; ++t) {
             if (t >= 3) {
                 const int target = sm.ycount[(t - 1) & 1][lane];
                 while (nsym_c < target) {
@@ -1433,55 +1477,41 @@ __global__ void __launch_bounds__(256) demod_ws3_kernel(const __grid_constant__ 
                 }
                 sm.ucount[t & 1][lane] = nsym_c;
             }
-        } else {
-            // ================= SLICER: the symbols COSTAS finished during tick t - 1 =================
+            ws3_tick_barrier();
+        }
+        if (active) { sp->costas_phase = cph; sp->costas_freq = cfr; sp->costas_ph2 = ph2; }
+    } else if (role == kRIdle) {
+        // placeholder warp of the 12-warp placements: keeps a scheduler slot empty, only counts barriers
+#pragma unroll 1
+        for (int t = -1; t <= t_last; ++t) { ws3_tick_barrier(); }
+    } else {
+        // ================= SLICER: the symbols COSTAS finished during tick t - 1 =================
+        SlicerState sl;
+        sl.prev = sp->prev_sym; sl.err_ptr = sp->err_ptr; sl.err_disp = sp->err_disp;
+        sl.err_partial = sp->err_partial; sl.standarderr = sp->standarderr; sl.sync = sp->sync;
+        sl.nsym = 0;
+        float err_blocks[TDM_SYNC_BLOCKS];
+#pragma unroll
+        for (int j = 0; j < TDM_SYNC_BLOCKS; ++j) { err_blocks[j] = sp->err_blocks[j]; }
+        const long long out_base = (long long)ch * p.out_stride;
+#pragma unroll 1
+        for (int t = -1; t <= t_last; ++t) {
             if (t >= 4) {
                 const int target = sm.ucount[(t - 1) & 1][lane];
                 do {    // one trip; more only if a tick ever carried over 5 symbols
                     slicer_symbols<5, kSymRing>(p, sm.us, lane, min(target - sl.nsym, 5), sl, err_blocks, active, out_base);
                 } while (__any_sync(0xffffffffu, sl.nsym < target));
             }
+            ws3_tick_barrier();
         }
-#ifdef TDM_ROLE_TIMING
-        work_cycles += clock64() - c0;
-#endif
-        __syncthreads();
-    }
-#ifdef TDM_ROLE_TIMING
-    if (blockIdx.x == 3 && lane == 0) {
-        unsigned wid, smid;
-        asm volatile("mov.u32 %0, %%warpid;" : "=r"(wid));
-        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
-        printf("ws3 role %d (hw warp slot %u on SM %u): work %lld of %lld cycles (%.1f%%), per tick %lld\n", role, wid, smid, work_cycles,
-               clock64() - t_begin, 100.0 * work_cycles / (double)(clock64() - t_begin), work_cycles / (nblk + 4));
-    }
-#endif
-
-    // ---- carry state out
-    if (!active) { return; }
-    if (role == kRLoop) {
-        sp->agc_gain = g; sp->fll_phase = fph; sp->fll_freq = ffr;
-        sp->n_samples += (unsigned long long)count;
-    } else if (role == kRPfar) {
-        float2* xh = reinterpret_cast<float2*>(sp->x_hist);
-        for (int m = 0; m < kHist; ++m) {
-            const long long q = (long long)count + m;
-            xh[m] = sm.xs[(int)((q / T) & (kWsXSlots - 1)) * T + (int)(q % T)][lane];
-        }
-    } else if (role == kRRrcA) {
-        float2* rh = reinterpret_cast<float2*>(sp->r_hist);
-        for (int j = 0; j < kITaps - 1; ++j) { rh[j] = sm.rs[(count + j) & (kWsREntries - 1)][lane]; }
-    } else if (role == kRTiming) {
-        sp->tr_mu = mu; sp->tr_omega = om; sp->tr_offset = offset - count;
-    } else if (role == kRCostas) {
-        sp->costas_phase = cph; sp->costas_freq = cfr; sp->costas_ph2 = ph2;
-    } else if (role == kRSlicer) {
-        sp->prev_sym = sl.prev; sp->err_ptr = sl.err_ptr; sp->err_disp = sl.err_disp;
-        sp->err_partial = sl.err_partial; sp->standarderr = sl.standarderr; sp->sync = sl.sync;
-        sp->n_symbols += (unsigned long long)sl.nsym;
+        if (active) {
+            sp->prev_sym = sl.prev; sp->err_ptr = sl.err_ptr; sp->err_disp = sl.err_disp;
+            sp->err_partial = sl.err_partial; sp->standarderr = sl.standarderr; sp->sync = sl.sync;
+            sp->n_symbols += (unsigned long long)sl.nsym;
 #pragma unroll
-        for (int j = 0; j < TDM_SYNC_BLOCKS; ++j) { sp->err_blocks[j] = err_blocks[j]; }
-        p.out_counts[ch] = sl.nsym;
+            for (int j = 0; j < TDM_SYNC_BLOCKS; ++j) { sp->err_blocks[j] = err_blocks[j]; }
+            p.out_counts[ch] = sl.nsym;
+        }
     }
 }
 
@@ -1495,13 +1525,16 @@ int launch_ws3(const DemodParams& p_in, cudaStream_t stream, int placement) {
         }
     }
     const int grid = (p.n_channels + 31) / 32;
-    auto go = [&](auto kern) {
+    auto go = [&](auto kern, int warps) {
         cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Ws3Smem));
-        kern<<<grid, 256, sizeof(Ws3Smem), stream>>>(p);
+        kern<<<grid, warps * 32, sizeof(Ws3Smem), stream>>>(p);
     };
-    if (placement == 1) { go(demod_ws3_kernel<1>); }
-    else if (placement == 2) { go(demod_ws3_kernel<2>); }
-    else { go(demod_ws3_kernel<0>); }
+    switch (placement) {
+        case 1: go(demod_ws3_kernel<1>, Ws3Placement<1>::warps); break;
+        case 2: go(demod_ws3_kernel<2>, Ws3Placement<2>::warps); break;
+        case 3: go(demod_ws3_kernel<3>, Ws3Placement<3>::warps); break;
+        default: go(demod_ws3_kernel<0>, Ws3Placement<0>::warps); break;
+    }
     return cudaGetLastError() == cudaSuccess ? 1 : -1;
 }
 
@@ -1541,6 +1574,7 @@ const char* demod_variant_name(int variant) {
         case 7: return "ws3";
         case 8: return "ws3-p1";
         case 9: return "ws3-p2";
+        case 10: return "ws3-p3";
         default: return "auto";
     }
 }
@@ -1561,6 +1595,7 @@ int launch_demod(const DemodParams& p, int variant, cudaStream_t stream) {
         case 7: return launch_ws3(p, stream, 0);
         case 8: return launch_ws3(p, stream, 1);
         case 9: return launch_ws3(p, stream, 2);
+        case 10: return launch_ws3(p, stream, 3);
         default: return -1;
     }
 }
