@@ -1035,20 +1035,20 @@ int launch_ws2(const DemodParams& p_in, cudaStream_t stream, int warps) {
 // Chains and their term order are unchanged (far -> previous block -> own block, ascending taps),
 // so the results are bit-identical to every other variant and to the canonical-order checker.
 // ---------------------------------------------------------------------------------------
-enum Ws3Role { kRLoop = 0, kRPfar = 1, kRQfar = 2, kRRrcA = 3, kRRrcB = 4, kRTiming = 5, kRCostas = 6, kRSlicer = 7, kRIdle = 8, kRAgc = 9 };
+enum Ws3Role { kRLoop = 0, kRPfar = 1, kRQfar = 2, kRRrcA = 3, kRRrcB = 4, kRTiming = 5, kRCostas = 6, kRSlicer = 7, kRIdle = 8, kRAgc = 9, kRMid = 10 };
 
 // warp -> role.  Warps w, w+4, w+8 share a scheduler (SMSP = warp slot mod 4 up to a rotation).
 template <int PLACEMENT>
 struct Ws3Placement {
     static constexpr unsigned long long r0 = kRLoop, rP = kRPfar, rQ = kRQfar, rA = kRRrcA, rB = kRRrcB, rT = kRTiming, rC = kRCostas,
-                                        rS = kRSlicer, rI = kRIdle, rG = kRAgc;
+                                        rS = kRSlicer, rI = kRIdle, rG = kRAgc, rM = kRMid;
     // one role per nibble, warp 0 in the lowest (a table indexed by the warp number would live in local memory).
     // 12 warps; columns = schedulers:        SMSP a     SMSP b     SMSP c     SMSP d
     static constexpr unsigned long long tab =
-        PLACEMENT == 0 ? (r0 | rT << 4 | rP << 8 | rQ << 12 |  rG << 16 | rC << 20 | rA << 24 | rB << 28 |  rI << 32 | rS << 36 | rI << 40 | rI << 44)
-      : PLACEMENT == 1 ? (r0 | rT << 4 | rP << 8 | rQ << 12 |  rI << 16 | rI << 20 | rA << 24 | rB << 28 |  rI << 32 | rG << 36 | rC << 40 | rS << 44)
-      : PLACEMENT == 2 ? (r0 | rT << 4 | rP << 8 | rQ << 12 |  rS << 16 | rG << 20 | rA << 24 | rB << 28 |  rI << 32 | rC << 36 | rI << 40 | rI << 44)
-      :                  (r0 | rP << 4 | rQ << 8 | rA << 12 |  rG << 16 | rT << 20 | rC << 24 | rB << 28 |  rI << 32 | rS << 36 | rI << 40 | rI << 44);
+        PLACEMENT == 0 ? (r0 | rP << 4 | rQ << 8 | rA << 12 |  rG << 16 | rT << 20 | rC << 24 | rB << 28 |  rS << 32 | rM << 36 | rI << 40 | rI << 44)
+      : PLACEMENT == 1 ? (r0 | rP << 4 | rQ << 8 | rA << 12 |  rG << 16 | rT << 20 | rC << 24 | rB << 28 |  rS << 32 | rI << 36 | rM << 40 | rI << 44)
+      : PLACEMENT == 2 ? (r0 | rP << 4 | rQ << 8 | rA << 12 |  rS << 16 | rT << 20 | rC << 24 | rB << 28 |  rM << 32 | rG << 36 | rI << 40 | rI << 44)
+      :                  (r0 | rP << 4 | rQ << 8 | rA << 12 |  rG << 16 | rT << 20 | rC << 24 | rB << 28 |  rM << 32 | rS << 36 | rI << 40 | rI << 44);
     static constexpr int warps = 12;
 };
 template <int PLACEMENT>
@@ -1235,6 +1235,10 @@ struct Ws3Smem {
 // from different program counters, whole warps at a time, the same number of times (ws3_ticks()).
 __device__ __forceinline__ void ws3_tick_barrier() { asm volatile("bar.sync 0;" ::: "memory"); }
 __device__ __forceinline__ int ws3_last_tick(int nblk) { return nblk + 3; }   // ticks run t = -1 .. nblk + 3
+// Named barrier 1 links MID (arrives, does not wait) and LOOP (waits) once per tick: 64 threads.
+__device__ __forceinline__ void ws3_mid_arrive() { asm volatile("bar.arrive 1, 64;" ::: "memory"); }
+__device__ __forceinline__ void ws3_mid_wait() { asm volatile("bar.sync 1, 64;" ::: "memory"); }
+constexpr int kMidOwn = 2;     // outputs of a block whose previous-block terms LOOP adds itself (needed before MID can deliver)
 
 template <int PLACEMENT>
 __global__ void __launch_bounds__(Ws3Placement<PLACEMENT>::warps * 32) demod_ws3_kernel(const __grid_constant__ DemodParams p) {
@@ -1326,51 +1330,70 @@ __global__ void __launch_bounds__(Ws3Placement<PLACEMENT>::warps * 32) demod_ws3
                 float2 ysc[T];
 #pragma unroll
                 for (int i = 0; i < T; ++i) { ysc[i] = sm.ysc[t & 1][i][lane]; }
-                // chains of this block's outputs: far part from the P/Q warps ...
+                // chains of this block's outputs: far part from the P/Q warps, then the previous block's 8 samples
+                // (sample j meets output i at tap 56 + j - i).  LOOP adds those only for the first kMidOwn outputs;
+                // the MID warp does the other outputs concurrently and hands them over through pfar/qfar (barrier 1).
                 float2 accP[T], accQ[T];
-#pragma unroll
-                for (int i = 0; i < T; ++i) { accP[i] = sm.pfar[t & 1][i][lane]; accQ[i] = sm.qfar[t & 1][i][lane]; }
                 const int mslot = (t + 7) & (kWsXSlots - 1);     // ring block of sample block t-1
                 const int xslot = (t + 8) & (kWsXSlots - 1);
                 if (valid == T) {
-                    // ... then the previous block's 8 samples (sample j meets output i at tap 56 + j - i) and the
-                    // block's own (sample i meets output q >= i at tap 64 + i - q), all in ONE basic block so the
-                    // scheduler can sink the 128 previous-block FFMA2 into the recurrence's latency shadow
                     {
                         float2 h[T];
 #pragma unroll
                         for (int j = 0; j < T; ++j) { h[j] = sm.xs[mslot * T + j][lane]; }
 #pragma unroll
+                        for (int i = 0; i < kMidOwn; ++i) { accP[i] = sm.pfar[t & 1][i][lane]; accQ[i] = sm.qfar[t & 1][i][lane]; }
+#pragma unroll
                         for (int j = 0; j < T; ++j) {
 #pragma unroll
-                            for (int i = 0; i < T; ++i) {
+                            for (int i = 0; i < kMidOwn; ++i) {
                                 accP[i] = fma2_rn(p.be_a[kHist - T + j - i], h[j], accP[i]);
                                 accQ[i] = fma2_rn(p.be_b[kHist - T + j - i], h[j], accQ[i]);
                             }
                         }
                     }
+                    float2 xo[kMidOwn];      // the block's first samples: their terms of the later outputs are added after the hand-over
+                    // the block's own samples (sample i meets output q >= i at tap 64 + i - q), straight line
 #pragma unroll
                     for (int i = 0; i < T; ++i) {
+                        if (i == kMidOwn) {
+                            ws3_mid_wait();
+#pragma unroll
+                            for (int q = kMidOwn; q < T; ++q) { accP[q] = sm.pfar[t & 1][q][lane]; accQ[q] = sm.qfar[t & 1][q][lane]; }
+#pragma unroll
+                            for (int j = 0; j < kMidOwn; ++j) {
+#pragma unroll
+                                for (int q = kMidOwn; q < T; ++q) {
+                                    accP[q] = fma2_rn(p.be_a[kHist + j - q], xo[j], accP[q]);
+                                    accQ[q] = fma2_rn(p.be_b[kHist + j - q], xo[j], accQ[q]);
+                                }
+                            }
+                        }
                         float sn, cs;
                         sincos_canon(fph, sn, cs);
                         const float yr = ysc[i].x, yi = ysc[i].y;
                         const float2 x = make_float2(fma_rn(yr, cs, mul_rn(yi, sn)), fma_rn(yi, cs, -mul_rn(yr, sn)));
                         sm.xs[xslot * T + i][lane] = x;
+                        if (i < kMidOwn) { xo[i] = x; }
 #pragma unroll
-                        for (int q = i; q < T; ++q) {
+                        for (int q = i; q < (i < kMidOwn ? kMidOwn : T); ++q) {
                             accP[q] = fma2_rn(p.be_a[kHist + i - q], x, accP[q]);
                             accQ[q] = fma2_rn(p.be_b[kHist + i - q], x, accQ[q]);
                         }
                         fll_update(lc, accP[i].x, accP[i].y, accQ[i].x, accQ[i].y, fph, ffr);
                     }
                 } else {
-                    // partial last block of a call: compact rolled code (previous block one sample per trip, then the
-                    // shift-register form in which position q always meets tap 64 - q)
+                    // partial last block of a call: compact rolled code.  MID has added the previous block's terms
+                    // to outputs kMidOwn.. ; the first outputs get theirs here, one sample per trip; then the
+                    // shift-register form in which position q always meets tap 64 - q.
+                    ws3_mid_wait();
+#pragma unroll
+                    for (int i = 0; i < T; ++i) { accP[i] = sm.pfar[t & 1][i][lane]; accQ[i] = sm.qfar[t & 1][i][lane]; }
 #pragma unroll 1
                     for (int j = 0; j < T; ++j) {
                         const float2 h = sm.xs[mslot * T + j][lane];
 #pragma unroll
-                        for (int i = 0; i < T; ++i) {
+                        for (int i = 0; i < kMidOwn; ++i) {
                             accP[i] = fma2_rn(p.be_a[kHist - T + j - i], h, accP[i]);
                             accQ[i] = fma2_rn(p.be_b[kHist - T + j - i], h, accQ[i]);
                         }
@@ -1396,6 +1419,32 @@ __global__ void __launch_bounds__(Ws3Placement<PLACEMENT>::warps * 32) demod_ws3
             ws3_tick_barrier();
         }
         if (active) { sp->fll_phase = fph; sp->fll_freq = ffr; }
+    } else if (role == kRMid) {
+        // ================= MID: previous block's terms of outputs kMidOwn..7 of block b = t, while LOOP runs its first samples =================
+        ws3_tick_barrier();                                  // tick t = -1
+#pragma unroll 1
+        for (int t = 0; t <= t_last; ++t) {
+            if (t < nblk) {
+                const int mslot = (t + 7) & (kWsXSlots - 1);
+                float2 h[T], aP[T - kMidOwn], aQ[T - kMidOwn];
+#pragma unroll
+                for (int j = 0; j < T; ++j) { h[j] = sm.xs[mslot * T + j][lane]; }
+#pragma unroll
+                for (int i = 0; i < T - kMidOwn; ++i) { aP[i] = sm.pfar[t & 1][kMidOwn + i][lane]; aQ[i] = sm.qfar[t & 1][kMidOwn + i][lane]; }
+#pragma unroll
+                for (int j = 0; j < T; ++j) {
+#pragma unroll
+                    for (int i = 0; i < T - kMidOwn; ++i) {
+                        aP[i] = fma2_rn(p.be_a[kHist - T + j - (kMidOwn + i)], h[j], aP[i]);
+                        aQ[i] = fma2_rn(p.be_b[kHist - T + j - (kMidOwn + i)], h[j], aQ[i]);
+                    }
+                }
+#pragma unroll
+                for (int i = 0; i < T - kMidOwn; ++i) { sm.pfar[t & 1][kMidOwn + i][lane] = aP[i]; sm.qfar[t & 1][kMidOwn + i][lane] = aQ[i]; }
+                ws3_mid_arrive();
+            }
+            ws3_tick_barrier();
+        }
     } else if (role == kRPfar || role == kRQfar) {
         // ================= P-far / Q-far: the oldest 56 - i terms of block b = t + 1 =================
         const int f = (role == kRPfar) ? 0 : 1;
@@ -1498,8 +1547,8 @@ __global__ void __launch_bounds__(Ws3Placement<PLACEMENT>::warps * 32) demod_ws3
         for (int t = -1; t <= t_last; ++t) {
             if (t >= 4) {
                 const int target = sm.ucount[(t - 1) & 1][lane];
-                do {    // one trip; more only if a tick ever carried over 5 symbols
-                    slicer_symbols<5, kSymRing>(p, sm.us, lane, min(target - sl.nsym, 5), sl, err_blocks, active, out_base);
+                do {    // one trip for the usual 4 symbols per 8-sample tick; a second when some lane has a fifth
+                    slicer_symbols<4, kSymRing>(p, sm.us, lane, min(target - sl.nsym, 4), sl, err_blocks, active, out_base);
                 } while (__any_sync(0xffffffffu, sl.nsym < target));
             }
             ws3_tick_barrier();
