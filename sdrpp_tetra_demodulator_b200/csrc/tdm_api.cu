@@ -54,7 +54,9 @@ struct tdm_handle {
     tdm_design design{};
     cudaStream_t own_stream = nullptr;
     cudaStream_t stream = nullptr;
+    cudaStream_t copy_stream = nullptr;          // host -> device staging of TDM_MEM_HOST calls, ahead of the kernels
     cudaEvent_t ev_start = nullptr, ev_stop = nullptr;
+    cudaEvent_t ev_slice[16] = {};               // slice k of the capture has landed in d_iq
     int variant = 0;
     long long launches = 0;
     // device memory owned by the handle
@@ -157,6 +159,10 @@ int tdm_create(const tdm_config* cfg, int32_t n_channels, int32_t max_chunk, int
     auto cleanup = [&](int code) { tdm_destroy(h); return code; };
     if (cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking) != cudaSuccess) { return cleanup(fail(TDM_ERR_CUDA, "cudaStreamCreate failed")); }
     h->stream = h->own_stream;
+    if (cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking) != cudaSuccess) { return cleanup(fail(TDM_ERR_CUDA, "cudaStreamCreate failed")); }
+    for (auto& e : h->ev_slice) {
+        if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) { return cleanup(fail(TDM_ERR_CUDA, "cudaEventCreate failed")); }
+    }
     if (cudaEventCreate(&h->ev_start) != cudaSuccess || cudaEventCreate(&h->ev_stop) != cudaSuccess) { return cleanup(fail(TDM_ERR_CUDA, "cudaEventCreate failed")); }
     if (cudaMalloc(&h->d_bank, sizeof(design.bank)) != cudaSuccess) { return cleanup(fail(TDM_ERR_NOMEM, "cudaMalloc(bank) failed")); }
     if (cudaMalloc(&h->d_states, sizeof(tdm_channel_state) * (size_t)n_channels) != cudaSuccess) { return cleanup(fail(TDM_ERR_NOMEM, "cudaMalloc(states) failed")); }
@@ -176,6 +182,8 @@ int tdm_destroy(tdm_handle* h) {
     cudaFree(h->d_dibits); cudaFree(h->d_bits); cudaFree(h->d_counts);
     if (h->ev_start) { cudaEventDestroy(h->ev_start); }
     if (h->ev_stop) { cudaEventDestroy(h->ev_stop); }
+    for (auto& e : h->ev_slice) { if (e) { cudaEventDestroy(e); } }
+    if (h->copy_stream) { cudaStreamDestroy(h->copy_stream); }
     if (h->own_stream) { cudaStreamDestroy(h->own_stream); }
     delete h;
     return TDM_OK;
@@ -221,6 +229,7 @@ int tdm_process(tdm_handle* h, const float* iq, int64_t in_stride, int32_t count
         p.bits = (out_flags & TDM_OUT_BITS) ? bits : nullptr;
         p.out_stride = out_stride;
         p.out_counts = out_counts;
+        p.accumulate = 0;
         TDM_CUDA(cudaEventRecord(h->ev_start, h->stream));
         const int n = tdm::launch_demod(p, h->variant, h->stream);
         if (n < 0) { return fail(TDM_ERR_CUDA, "demod kernel launch failed: %s", cudaGetErrorString(cudaGetLastError())); }
@@ -234,21 +243,46 @@ int tdm_process(tdm_handle* h, const float* iq, int64_t in_stride, int32_t count
     int rc = ensure_staging(h, out_flags);
     if (rc != TDM_OK) { return rc; }
     const long long dstride = h->max_syms;      // staging rows are max_syms wide
-    if (count > 0) {
-        TDM_CUDA(cudaMemcpy2DAsync(h->d_iq, sizeof(float2) * (size_t)count, iq, sizeof(float2) * (size_t)in_stride,
-                                   sizeof(float2) * (size_t)count, C, cudaMemcpyHostToDevice, h->stream));
-    }
-    p.iq = h->d_iq;
-    p.in_stride = count;
     p.syms = (out_flags & TDM_OUT_SYMBOLS) ? h->d_syms : nullptr;
     p.dibits = (out_flags & TDM_OUT_DIBITS) ? h->d_dibits : nullptr;
     p.bits = (out_flags & TDM_OUT_BITS) ? h->d_bits : nullptr;
     p.out_stride = dstride;
     p.out_counts = h->d_counts;
+    p.in_stride = count;
+    // The capture is cut into time slices: slice k+1 crosses PCIe (copy stream) while slice k is demodulated
+    // (handle stream).  The chain is chunk invariant bit for bit -- every kernel carries its state in
+    // tdm_channel_state -- so slicing changes nothing but the overlap; slices after the first append to the
+    // output rows (DemodParams::accumulate).  A call is PCIe bound (8 B in per sample against 0.5 B out), so
+    // hiding the kernel behind the copy is all there is to win.
+    constexpr int kMaxSlices = (int)(sizeof(h->ev_slice) / sizeof(h->ev_slice[0]));
+    int slice_len = count;
+    if (count >= 16384) {
+        slice_len = (count + 7) / 8;
+        if (slice_len < 8192) { slice_len = 8192; }
+        slice_len = (slice_len + 63) & ~63;                  // whole 8-sample blocks, aligned rows
+    }
+    const int n_slices = count > 0 ? (count + slice_len - 1) / slice_len : 1;
+    if (n_slices > kMaxSlices) { return fail(TDM_ERR_ARG, "tdm_process: internal slice count"); }
+    // the copy stream must not overtake work already queued on the handle's stream that still reads d_iq
+    TDM_CUDA(cudaEventRecord(h->ev_slice[0], h->stream));
+    TDM_CUDA(cudaStreamWaitEvent(h->copy_stream, h->ev_slice[0], 0));
     TDM_CUDA(cudaEventRecord(h->ev_start, h->stream));
-    const int n = tdm::launch_demod(p, h->variant, h->stream);
-    if (n < 0) { return fail(TDM_ERR_CUDA, "demod kernel launch failed: %s", cudaGetErrorString(cudaGetLastError())); }
-    h->launches += n;
+    for (int k = 0; k < n_slices; ++k) {
+        const int off = k * slice_len;
+        const int len = (count - off < slice_len) ? count - off : slice_len;
+        if (len > 0) {
+            TDM_CUDA(cudaMemcpy2DAsync(h->d_iq + off, sizeof(float2) * (size_t)count, iq + 2 * (size_t)off, sizeof(float2) * (size_t)in_stride,
+                                       sizeof(float2) * (size_t)len, C, cudaMemcpyHostToDevice, h->copy_stream));
+        }
+        TDM_CUDA(cudaEventRecord(h->ev_slice[k], h->copy_stream));
+        TDM_CUDA(cudaStreamWaitEvent(h->stream, h->ev_slice[k], 0));
+        p.iq = h->d_iq + off;
+        p.count = len;
+        p.accumulate = (k > 0) ? 1 : 0;
+        const int n = tdm::launch_demod(p, h->variant, h->stream);
+        if (n < 0) { return fail(TDM_ERR_CUDA, "demod kernel launch failed: %s", cudaGetErrorString(cudaGetLastError())); }
+        h->launches += n;
+    }
     TDM_CUDA(cudaEventRecord(h->ev_stop, h->stream));
     // Only the part of each row a call of `count` samples can fill is copied back.
     const size_t w = (size_t)need;

@@ -58,6 +58,7 @@ struct SymbolState {
     float err_partial, standarderr;
     uint32_t sync;
     int nsym;
+    int out_room;      // symbols this call may still write into the channel's output rows
 };
 
 // Loop gains/limits of the symbol-rate loops, pinned in registers by the role that runs do_symbol().
@@ -164,7 +165,7 @@ __device__ __forceinline__ void costas_step(const DemodParams& p, const SymConst
     const uint32_t pd = (sym - st.prev + 4u) & 3u;
     const uint32_t db = pd ^ (pd >> 1);          // 0,1,2,3 -> 0,1,3,2
     st.prev = sym;
-    if (active && st.nsym < p.out_stride) {   // rows are sized by tdm_max_symbols(); never write past one
+    if (active && st.nsym < st.out_room) {   // rows are sized by tdm_max_symbols(); never write past one
         const long long o = out_base + st.nsym;
         if (p.syms) { p.syms[o] = make_float2(ur, ui); }
         if (p.dibits) { p.dibits[o] = (uint8_t)db; }
@@ -254,7 +255,9 @@ __global__ void __launch_bounds__(128) demod_tpc_kernel(const __grid_constant__ 
     st.cph = sp->costas_phase; st.cfr = sp->costas_freq; st.ph2 = sp->costas_ph2;
     st.prev = sp->prev_sym; st.err_ptr = sp->err_ptr; st.err_disp = sp->err_disp;
     st.err_partial = sp->err_partial; st.standarderr = sp->standarderr; st.sync = sp->sync;
-    st.nsym = 0;
+    const int nsym0 = p.accumulate ? p.out_counts[ch] : 0;       // time-sliced calls append to the rows (tdm_api.cu)
+    const long long out_base = (long long)ch * p.out_stride + nsym0;
+    st.nsym = 0; st.out_room = (int)p.out_stride - nsym0;
     float err_blocks[TDM_SYNC_BLOCKS];
 #pragma unroll
     for (int j = 0; j < TDM_SYNC_BLOCKS; ++j) { err_blocks[j] = sp->err_blocks[j]; }
@@ -269,7 +272,6 @@ __global__ void __launch_bounds__(128) demod_tpc_kernel(const __grid_constant__ 
     __syncthreads();   // bank_s visible
 
     const float2* __restrict__ in = p.iq + (long long)ch * p.in_stride;
-    const long long out_base = (long long)ch * p.out_stride;
     const int count = p.count;
     const int nblk = (count + T - 1) / T;
 
@@ -385,7 +387,7 @@ __global__ void __launch_bounds__(128) demod_tpc_kernel(const __grid_constant__ 
         }
         float2* rh = reinterpret_cast<float2*>(sp->r_hist);
         for (int j = 0; j < kITaps - 1; ++j) { rh[j] = rs[((count + j) & (RE - 1)) * 32 + lane]; }
-        p.out_counts[ch] = st.nsym;
+        p.out_counts[ch] = nsym0 + st.nsym;
     }
 }
 
@@ -507,7 +509,8 @@ __global__ void __launch_bounds__(160) demod_ws_kernel(const __grid_constant__ D
     const float2* __restrict__ in = p.iq + (long long)ch * p.in_stride;
     SymbolState st;
     float err_blocks[TDM_SYNC_BLOCKS];
-    const long long out_base = (long long)ch * p.out_stride;
+    const int nsym0 = p.accumulate ? p.out_counts[ch] : 0;       // time-sliced calls append to the rows (tdm_api.cu)
+    const long long out_base = (long long)ch * p.out_stride + nsym0;
     LoopConsts lc = {};
     SymConsts kc = {};
     float tria[T], trib[T];                 // taps 64-q of the band-edge pair: the newest terms, in registers
@@ -526,7 +529,7 @@ __global__ void __launch_bounds__(160) demod_ws_kernel(const __grid_constant__ D
         st.cph = sp->costas_phase; st.cfr = sp->costas_freq; st.ph2 = sp->costas_ph2;
         st.prev = sp->prev_sym; st.err_ptr = sp->err_ptr; st.err_disp = sp->err_disp;
         st.err_partial = sp->err_partial; st.standarderr = sp->standarderr; st.sync = sp->sync;
-        st.nsym = 0;
+        st.nsym = 0; st.out_room = (int)p.out_stride - nsym0;
 #pragma unroll
         for (int j = 0; j < TDM_SYNC_BLOCKS; ++j) { err_blocks[j] = sp->err_blocks[j]; }
         kc = load_sym_consts(p);
@@ -679,7 +682,7 @@ __global__ void __launch_bounds__(160) demod_ws_kernel(const __grid_constant__ D
         sp->n_symbols += (unsigned long long)st.nsym;
 #pragma unroll
         for (int j = 0; j < TDM_SYNC_BLOCKS; ++j) { sp->err_blocks[j] = err_blocks[j]; }
-        p.out_counts[ch] = st.nsym;
+        p.out_counts[ch] = nsym0 + st.nsym;
     }
 }
 
@@ -814,13 +817,14 @@ __global__ void __launch_bounds__(WARPS * 32) demod_ws2_kernel(const __grid_cons
     }
     SymbolState st;
     float err_blocks[TDM_SYNC_BLOCKS];
-    const long long out_base = (long long)ch * p.out_stride;
+    const int nsym0 = p.accumulate ? p.out_counts[ch] : 0;       // time-sliced calls append to the rows (tdm_api.cu)
+    const long long out_base = (long long)ch * p.out_stride + nsym0;
     if (role == 5) {
         st.mu = 0.f; st.om = 0.f; st.offset = 0;
         st.cph = sp->costas_phase; st.cfr = sp->costas_freq; st.ph2 = sp->costas_ph2;
         st.prev = sp->prev_sym; st.err_ptr = sp->err_ptr; st.err_disp = sp->err_disp;
         st.err_partial = sp->err_partial; st.standarderr = sp->standarderr; st.sync = sp->sync;
-        st.nsym = 0;
+        st.nsym = 0; st.out_room = (int)p.out_stride - nsym0;
 #pragma unroll
         for (int j = 0; j < TDM_SYNC_BLOCKS; ++j) { err_blocks[j] = sp->err_blocks[j]; }
         kc = load_sym_consts(p);
@@ -991,7 +995,7 @@ __global__ void __launch_bounds__(WARPS * 32) demod_ws2_kernel(const __grid_cons
         sp->n_symbols += (unsigned long long)st.nsym;
 #pragma unroll
         for (int j = 0; j < TDM_SYNC_BLOCKS; ++j) { sp->err_blocks[j] = err_blocks[j]; }
-        p.out_counts[ch] = st.nsym;
+        p.out_counts[ch] = nsym0 + st.nsym;
     }
 }
 
@@ -1169,6 +1173,7 @@ struct SlicerState {
     float err_partial, standarderr;
     uint32_t sync;
     int nsym;
+    int out_room;
 };
 template <int NS, int RING>
 __device__ __forceinline__ void slicer_symbols(const DemodParams& p, const float2 (*us)[32], int lane, int n, SlicerState& sl,
@@ -1198,7 +1203,7 @@ __device__ __forceinline__ void slicer_symbols(const DemodParams& p, const float
         const uint32_t pd = (sym - sl.prev + 4u) & 3u;
         const uint32_t db = pd ^ (pd >> 1);          // 0,1,2,3 -> 0,1,3,2
         sl.prev = v ? sym : sl.prev;
-        if (v && active && base + k < p.out_stride) {   // rows are sized by tdm_max_symbols(); never write past one
+        if (v && active && base + k < sl.out_room) {   // rows are sized by tdm_max_symbols(); never write past one
             const long long o = out_base + base + k;
             if (p.syms) { p.syms[o] = u; }
             if (p.dibits) { p.dibits[o] = (uint8_t)db; }
@@ -1538,11 +1543,12 @@ __global__ void __launch_bounds__(Ws3Placement<PLACEMENT>::warps * 32) demod_ws3
         SlicerState sl;
         sl.prev = sp->prev_sym; sl.err_ptr = sp->err_ptr; sl.err_disp = sp->err_disp;
         sl.err_partial = sp->err_partial; sl.standarderr = sp->standarderr; sl.sync = sp->sync;
-        sl.nsym = 0;
+        const int nsym0 = p.accumulate ? p.out_counts[ch] : 0;       // time-sliced calls append to the rows (tdm_api.cu)
+        const long long out_base = (long long)ch * p.out_stride + nsym0;
+        sl.nsym = 0; sl.out_room = (int)p.out_stride - nsym0;
         float err_blocks[TDM_SYNC_BLOCKS];
 #pragma unroll
         for (int j = 0; j < TDM_SYNC_BLOCKS; ++j) { err_blocks[j] = sp->err_blocks[j]; }
-        const long long out_base = (long long)ch * p.out_stride;
 #pragma unroll 1
         for (int t = -1; t <= t_last; ++t) {
             if (t >= 4) {
@@ -1559,7 +1565,7 @@ __global__ void __launch_bounds__(Ws3Placement<PLACEMENT>::warps * 32) demod_ws3
             sp->n_symbols += (unsigned long long)sl.nsym;
 #pragma unroll
             for (int j = 0; j < TDM_SYNC_BLOCKS; ++j) { sp->err_blocks[j] = err_blocks[j]; }
-            p.out_counts[ch] = sl.nsym;
+            p.out_counts[ch] = nsym0 + sl.nsym;
         }
     }
 }
@@ -1630,10 +1636,10 @@ const char* demod_variant_name(int variant) {
 
 int launch_demod(const DemodParams& p, int variant, cudaStream_t stream) {
     if (p.n_channels <= 0) { return 0; }
-    // auto: the warp-specialised pipeline wins while channels are scarce (it puts 6 warps behind every 32
-    // channels); once there are enough channels to fill every scheduler with plain thread-per-channel warps,
-    // the monolithic kernel's lower instruction count wins.
-    if (variant == 0) { variant = (p.n_channels >= 16384) ? 2 : 5; }
+    // auto: the warp-specialised pipeline (ws3: 12 role warps behind every 32 channels, one CTA per SM) wins
+    // while channels are scarce; once there are enough channels to fill every scheduler with plain
+    // thread-per-channel warps, the monolithic kernel's lower instruction count per sample wins.
+    if (variant == 0) { variant = (p.n_channels >= 16384) ? 2 : 8; }
     switch (variant) {
         case 1: return launch_tpc<4>(p, stream, 1);
         case 2: return launch_tpc<8>(p, stream, 1);

@@ -35,6 +35,8 @@ struct DemodParams {
     uint8_t* bits;                  // [C][2*out_stride] or nullptr
     long long out_stride;
     int* out_counts;                // [C]
+    int accumulate;                 // 0: rows are written from symbol 0 and out_counts is overwritten;
+                                    // 1: append after the out_counts[c] symbols already there (time slices of one call)
     tdm_channel_state* states;      // [C]
 };
 
