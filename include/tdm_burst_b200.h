@@ -112,6 +112,9 @@ int tdm_bsync_in(tdm_bsync* h, const uint8_t* in, int64_t in_stride, const int32
 int tdm_bsync_get_state(tdm_bsync* h, tdm_bsync_state* host_states, int32_t n_channels);
 int tdm_bsync_set_state(tdm_bsync* h, const tdm_bsync_state* host_states, int32_t n_channels);
 int64_t tdm_bsync_launch_count(const tdm_bsync* h);
+/* Device time in ms of the three kernels of the most recent tdm_bsync_in (pack, detect, sync), measured with CUDA
+ * events on the handle's stream (synchronises).  Benchmarking / profiling only. */
+int tdm_bsync_last_kernel_ms(tdm_bsync* h, float* ms3);
 
 /* tetra_find_train_seq for C independent buffers of one bit per byte, including its look-ahead quirk: the
  * 22-bit pre-filter (tetra_burst.c:289-307) is preloaded one bit short, so for the first 21 positions it does

@@ -41,6 +41,17 @@ EXPORTED_SYMBOLS = [
     "tdm_get_metrics", "tdm_set_config", "tdm_get_design", "tdm_set_kernel_variant", "tdm_last_kernel_ms",
     "tdm_launch_count", "tdm_pack_dibits", "tdm_synth_capture", "tdm_last_error", "tdm_abi_version",
 ]
+# ... and include/tdm_burst_b200.h
+EXPORTED_BURST_SYMBOLS = [
+    "tdm_bsync_create", "tdm_bsync_destroy", "tdm_bsync_set_stream", "tdm_bsync_reset", "tdm_bsync_in",
+    "tdm_bsync_get_state", "tdm_bsync_set_state", "tdm_bsync_launch_count", "tdm_bsync_last_kernel_ms", "tdm_find_train_seq", "tdm_burst_demux",
+]
+
+TDM_BITS_PER_TS = 510
+TDM_BSYNC_MAX_CALL_BITS = 510
+TDM_TRAIN_NORM_1, TDM_TRAIN_NORM_2, TDM_TRAIN_NORM_3, TDM_TRAIN_SYNC, TDM_TRAIN_EXT = 0, 1, 2, 3, 4
+TDM_RX_S_UNLOCKED, TDM_RX_S_KNOW_FSTART, TDM_RX_S_LOCKED = 0, 1, 2
+TDM_BSYNC_IN_BITS, TDM_BSYNC_IN_DIBITS = 0, 1
 
 
 class TdmConfig(C.Structure):
@@ -88,6 +99,15 @@ STATE_DTYPE = np.dtype([
     ("err_blocks", "<f4", (TDM_SYNC_BLOCKS,)), ("x_hist", "<f4", (2 * TDM_HIST,)),
     ("r_hist", "<f4", (2 * (TDM_INTERP_TAPS - 1),)), ("reserved1", "<f4", (2,)),
 ], align=True)
+# numpy views of tdm_burst / tdm_bsync_state / tdm_tp_sap_block (include/tdm_burst_b200.h)
+BURST_DTYPE = np.dtype([("bitnum", "<u4"), ("train_seq", "<i4"), ("tn", "<u4"), ("fn", "<u4"), ("mn", "<u4"),
+                        ("call_index", "<u4"), ("reserved", "<u4", (2,)), ("bits", "u1", (512,))], align=True)
+BSYNC_STATE_DTYPE = np.dtype([("state", "<i4"), ("bits_in_buf", "<u4"), ("bitbuf_start_bitnum", "<u4"),
+                              ("next_frame_start_bitnum", "<u4"), ("tn", "<u4"), ("fn", "<u4"), ("mn", "<u4"),
+                              ("ts_found", "<u4"), ("ts_expire", "<u4"), ("ts_window_lo", "<u4"), ("ts_window_hi", "<u4"),
+                              ("searched_upto", "<u4"), ("n_bits", "<u8"), ("n_bursts", "<u8"), ("bitbuf", "<u4", (128,))],
+                             align=True)
+TP_SAP_BLOCK_DTYPE = np.dtype([("type", "<i4"), ("blk_num", "<i4"), ("n_bits", "<i4"), ("bits", "u1", (432,))], align=True)
 METRICS_DTYPE = np.dtype([("standarderr", "<f4"), ("sync", "<u4"), ("n_samples", "<u8"), ("n_symbols", "<u8")],
                          align=True)
 
@@ -134,6 +154,17 @@ def lib() -> C.CDLL:
         "tdm_synth_capture": (C.c_int, [i32, vp, C.POINTER(TdmSynthParams), i32, i64, i64, i32, vp, vp, i64]),
         "tdm_last_error": (C.c_char_p, []),
         "tdm_abi_version": (C.c_int, []),
+        "tdm_bsync_create": (C.c_int, [i32, i64, i32, C.POINTER(vp)]),
+        "tdm_bsync_destroy": (C.c_int, [vp]),
+        "tdm_bsync_set_stream": (C.c_int, [vp, vp]),
+        "tdm_bsync_reset": (C.c_int, [vp]),
+        "tdm_bsync_in": (C.c_int, [vp, vp, i64, vp, i32, i32, i32, vp, i32, vp, i32, i32]),
+        "tdm_bsync_get_state": (C.c_int, [vp, vp, i32]),
+        "tdm_bsync_set_state": (C.c_int, [vp, vp, i32]),
+        "tdm_bsync_launch_count": (i64, [vp]),
+        "tdm_bsync_last_kernel_ms": (C.c_int, [vp, C.POINTER(C.c_float)]),
+        "tdm_find_train_seq": (C.c_int, [i32, vp, vp, i64, i32, u32, u32, vp, vp, i32]),
+        "tdm_burst_demux": (C.c_int, [vp, vp]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)

@@ -12,6 +12,7 @@
 #include <vector>
 #include "tdm_b200.h"
 #include "tdm_kernels.cuh"
+#include "tdm_internal.h"
 
 namespace {
 
@@ -44,6 +45,14 @@ struct DeviceGuard {
 };
 
 }  // namespace
+
+int tdm_internal_fail(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
 
 struct tdm_handle {
     int device = 0;

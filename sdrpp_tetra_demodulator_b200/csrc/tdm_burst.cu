@@ -1,0 +1,690 @@
+// tdm_burst.cu -- burst synchroniser for C channels on sm_100a (C ABI: include/tdm_burst_b200.h).
+//
+// Reference behaviour (paths relative to the reference tree):
+//   tetra_find_train_seq    src/decoder/src/phy/tetra_burst.c:271-341
+//   tetra_burst_sync_in     src/decoder/src/phy/tetra_burst_sync.c:54-155   (+ make_bitbuf_space :38-51)
+//   tetra_tdma_time_add_tn  src/decoder/src/tetra_tdma.c:44-74
+//   _demodSinkHandler       src/main.cpp:385-414                            (training-sequence detector)
+//
+// The reference keeps a 4096-byte bit buffer per receiver, memmoves it on every call and memcmps byte
+// strings.  A receiver's buffer is always a WINDOW of its bit stream (bits are appended at the end and dropped
+// at the front), so here the stream is packed once, 1 bit per bit, and the buffer is two numbers: where the
+// window starts and how long it is.  Three kernels per tdm_bsync_in:
+//
+//   pack    (HBM bound: reads 1 byte per input unit, writes 1/8 byte per bit)  -- every (channel, 4096-bit tile)
+//           in parallel: 16-byte loads, 16 bytes -> 16 (or 32) bits with one multiply per 4 bytes, re-aligned
+//           through shared memory behind the channel's carried bits;
+//   detect  (optional, bit-parallel) -- every (channel, 32 positions): the eight training sequences are matched
+//           against 32 window positions at once with funnel shifts and AND/ANDN, early exit when no candidate
+//           position is left;
+//   sync    one warp per channel replays the reference's calls: the state machine is scalar (warp uniform),
+//           every search is 32 positions per step with 64-bit window compares and a ballot.
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstring>
+#include <new>
+#include <vector>
+#include "tdm_b200.h"
+#include "tdm_burst_b200.h"
+#include "tdm_internal.h"
+
+namespace {
+
+constexpr int kTileBits = 4096;                 // logical bits per pack CTA
+constexpr int kTileWords = kTileBits / 32;
+constexpr int kPadWords = 8;                    // readable words past the last bit of a row (64-bit window loads)
+
+// training sequences as left-aligned numbers (first bit = most significant), phy/tetra_burst.c:61-72
+constexpr unsigned long long seq_bits(const int* b, int n) {
+    unsigned long long v = 0;
+    for (int i = 0; i < n; ++i) { v = (v << 1) | (unsigned long long)b[i]; }
+    return v;
+}
+constexpr int kN[22] = { 1,1, 0,1, 0,0, 0,0, 1,1, 1,0, 1,0, 0,1, 1,1, 0,1, 0,0 };
+constexpr int kP[22] = { 0,1, 1,1, 1,0, 1,0, 0,1, 0,0, 0,0, 1,1, 0,1, 1,1, 1,0 };
+constexpr int kQ[22] = { 1,0, 1,1, 0,1, 1,1, 0,0, 0,0, 0,1, 1,0, 1,0, 1,1, 0,1 };
+constexpr int kNN[33] = { 1,1,1, 0,0,1, 1,0,1, 1,1,1, 0,0,0, 1,1,1, 1,0,0, 0,1,1, 1,1,0, 0,0,0, 0,0,0 };
+constexpr int kPP[33] = { 1,0,1, 0,1,1, 1,1,1, 1,0,1, 0,1,0, 1,0,1, 1,1,0, 0,0,1, 1,0,0, 0,1,0, 0,1,0 };
+constexpr int kX[30] = { 1,0, 0,1, 1,1, 0,1, 0,0, 0,0, 1,1, 1,0, 1,0, 0,1, 1,1, 0,1, 0,0, 0,0, 1,1 };
+constexpr int kXX[45] = { 0,1,1,1,0,0,1,1,0,1,0,0,0,0,1,0,0,0,1,1,1,0,1,1,0,1,0,1,0,1,1,1,1,1,0,1,0,0,0,0,0,1,1,1,0 };
+constexpr int kY[38] = { 1,1, 0,0, 0,0, 0,1, 1,0, 0,1, 1,1, 0,0, 1,1, 1,0, 1,0, 0,1, 1,1, 0,0, 0,0, 0,1, 1,0, 0,1, 1,1 };
+constexpr unsigned long long kSeqN = seq_bits(kN, 22), kSeqP = seq_bits(kP, 22), kSeqQ = seq_bits(kQ, 22);
+constexpr unsigned long long kSeqNN = seq_bits(kNN, 33), kSeqPP = seq_bits(kPP, 33), kSeqX = seq_bits(kX, 30);
+constexpr unsigned long long kSeqXX = seq_bits(kXX, 45), kSeqY = seq_bits(kY, 38);
+constexpr uint32_t kPreY = (uint32_t)(kSeqY >> 16), kPreX = (uint32_t)(kSeqX >> 8);   // first 22 bits
+
+struct BsyncParams {
+    const uint8_t* in;            // [C][in_stride] bytes
+    long long in_stride;
+    const int* n_units;           // [C] or null
+    int units_all;
+    int max_units;                // rows of wb are sized for this many units: per-channel counts are clamped to it
+    int bits_per_unit;            // 1 or 2
+    int n_channels;
+    tdm_bsync_state* states;      // null for the stateless find
+    uint32_t* wb;                 // [C][wstride] packed work rows: carried bits then the new bits
+    long long wstride;
+    int* last_hit;                // [C] detector: 1 + index of the last new bit that completed a sequence, 0 = none
+    int call_bits;
+    tdm_burst* bursts;
+    int max_bursts;
+    int* n_bursts;
+    int detect_ts;
+    // stateless find
+    uint32_t find_end, find_mask;
+    int* find_type;
+    uint32_t* find_offset;
+};
+
+__device__ __forceinline__ int units_of(const BsyncParams& p, int c) {
+    int u = p.n_units ? p.n_units[c] : p.units_all;
+    u = u < 0 ? 0 : u;
+    return u > p.max_units ? p.max_units : u;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// pack: logical row = [carried bits (state.bitbuf, bits_in_buf of them)] ++ [new bits], MSB first.
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t pack4_bits(uint32_t x) { return (((x & 0x01010101u) * 0x08040201u) >> 24) & 0xfu; }
+__device__ __forceinline__ uint32_t pack4_dibits(uint32_t x) { return (((x & 0x03030303u) * 0x40100401u) >> 24) & 0xffu; }
+
+__global__ void __launch_bounds__(256) bsync_pack_kernel(const BsyncParams p) {
+    __shared__ uint16_t s16[2 * 132 + 8];
+    const int c = blockIdx.y;
+    const int bpu = p.bits_per_unit;
+    const int nu = units_of(p, c);
+    const long long nbits = (long long)nu * bpu;
+    const int cl = p.states ? (int)p.states[c].bits_in_buf : 0;
+    const long long total = cl + nbits;
+    const long long tile0 = (long long)blockIdx.x * kTileBits;              // first logical bit of this tile
+    if (blockIdx.x == 0 && threadIdx.x == 0 && p.last_hit) { p.last_hit[c] = 0; }
+    if (tile0 >= total + 32 * kPadWords) { return; }
+    const uint8_t* __restrict__ row = p.in + (long long)c * p.in_stride;
+    const long long ib0 = tile0 - cl;                                       // first input bit of the tile (may be < 0)
+    long long u0 = ib0 >= 0 ? ib0 / bpu : -((-ib0 + bpu - 1) / bpu);        // floor(ib0 / bpu)
+    const long long A = u0 & ~15LL;                                         // aligned first unit staged
+    const int groups = (bpu == 1) ? 257 : 129;                              // 16 units each
+    const bool aligned = ((reinterpret_cast<uintptr_t>(row) & 15u) == 0);
+    for (int g = threadIdx.x; g < groups; g += blockDim.x) {
+        const long long ua = A + 16LL * g;
+        uint32_t w[4] = { 0, 0, 0, 0 };
+        if (ua >= 0 && ua + 16 <= nu && aligned) {
+            const uint4 v = __ldg(reinterpret_cast<const uint4*>(row + ua));
+            w[0] = v.x; w[1] = v.y; w[2] = v.z; w[3] = v.w;
+        } else if (ua + 16 > 0 && ua < nu) {
+#pragma unroll
+            for (int k = 0; k < 16; ++k) {
+                const long long u = ua + k;
+                const uint32_t b = (u >= 0 && u < nu) ? (uint32_t)row[u] : 0u;
+                w[k >> 2] |= b << (8 * (k & 3));
+            }
+        }
+        if (bpu == 1) {
+            s16[g] = (uint16_t)((pack4_bits(w[0]) << 12) | (pack4_bits(w[1]) << 8) | (pack4_bits(w[2]) << 4) | pack4_bits(w[3]));
+        } else {
+            s16[2 * g] = (uint16_t)((pack4_dibits(w[0]) << 8) | pack4_dibits(w[1]));
+            s16[2 * g + 1] = (uint16_t)((pack4_dibits(w[2]) << 8) | pack4_dibits(w[3]));
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x < kTileWords) {
+        const int t = threadIdx.x;
+        const long long wi = (long long)blockIdx.x * kTileWords + t;
+        if (wi * 32 < total + 32 * kPadWords && wi < p.wstride) {
+            const int o = (int)(ib0 - A * bpu) + 32 * t;                    // bit offset into the staged bits
+            const int idx = o >> 4, sh = o & 15;
+            const unsigned long long v = ((unsigned long long)s16[idx] << 32) | ((unsigned long long)s16[idx + 1] << 16) | s16[idx + 2];
+            uint32_t word = (uint32_t)(v >> (16 - sh));
+            if (p.states && wi * 32 < cl) { word |= p.states[c].bitbuf[wi]; }   // carried bits (zero beyond bits_in_buf)
+            p.wb[(long long)c * p.wstride + wi] = word;
+        }
+    }
+}
+
+// 64 bits of a packed row starting at bit position pos (first bit in bit 63)
+__device__ __forceinline__ unsigned long long load64(const uint32_t* __restrict__ rowp, long long pos) {
+    const long long wi = pos >> 5;
+    const int sh = (int)(pos & 31);
+    const uint32_t w0 = rowp[wi], w1 = rowp[wi + 1], w2 = rowp[wi + 2];
+    const uint32_t hi = __funnelshift_l(w1, w0, sh), lo = __funnelshift_l(w2, w1, sh);
+    return ((unsigned long long)hi << 32) | lo;
+}
+
+// which enabled sequence starts at a window W with `rem` bits left in the buffer; -1 = none.
+// Order of the tests as in tetra_burst.c:309-338.
+__device__ __forceinline__ int match_train_seq(unsigned long long W, uint32_t rem, uint32_t mask) {
+    if ((mask & (1u << TDM_TRAIN_SYNC)) && rem >= 38 && (W >> 26) == kSeqY) { return TDM_TRAIN_SYNC; }
+    if ((mask & (1u << TDM_TRAIN_NORM_1)) && rem >= 22 && (W >> 42) == kSeqN) { return TDM_TRAIN_NORM_1; }
+    if ((mask & (1u << TDM_TRAIN_NORM_2)) && rem >= 22 && (W >> 42) == kSeqP) { return TDM_TRAIN_NORM_2; }
+    if ((mask & (1u << TDM_TRAIN_NORM_3)) && rem >= 22 && (W >> 42) == kSeqQ) { return TDM_TRAIN_NORM_3; }
+    if ((mask & (1u << TDM_TRAIN_EXT)) && rem >= 30 && (W >> 34) == kSeqX) { return TDM_TRAIN_EXT; }
+    return -1;
+}
+
+// tetra_find_train_seq over buffer [ps, ps + len) of a packed row, by one warp.  `from` = first position >= ps + 21
+// that still has to be examined with the plain rule (earlier ones are known not to hold an enabled sequence).
+// Returns the type (warp uniform) and the offset relative to ps.
+__device__ __forceinline__ int warp_find_train_seq(const uint32_t* __restrict__ rowp, long long ps, uint32_t len, uint32_t mask,
+                                                   long long from, uint32_t& offset) {
+    const int lane = threadIdx.x & 31;
+    if (len < 22) { return -1; }
+    // positions 0..20: the reference's look-ahead register does not hold in[i..i+21] there (one bit short preload,
+    // tetra_burst.c:292-300): it holds in[i-1..19] ++ in[21..21+i] (a leading 0 for i = 0); the position is examined
+    // only if THAT equals the first 22 bits of y, n, p, q or x.
+    {
+        const unsigned long long W0 = load64(rowp, ps);
+        int t = -1;
+        if (lane <= 20 && len - (uint32_t)lane >= 22) {
+            const int i = lane;
+            const uint32_t part1 = (uint32_t)(W0 >> 44) & ((1u << (21 - i)) - 1u);
+            const uint32_t part2 = (uint32_t)(W0 >> (42 - i)) & ((1u << (i + 1)) - 1u);
+            const uint32_t f = (part1 << (i + 1)) | part2;
+            const bool pass = f == kPreY || f == (uint32_t)kSeqN || f == (uint32_t)kSeqP || f == (uint32_t)kSeqQ || f == kPreX;
+            if (pass) { t = match_train_seq(load64(rowp, ps + i), len - (uint32_t)i, mask); }
+        }
+        const unsigned hit = __ballot_sync(0xffffffffu, t >= 0);
+        if (hit) {
+            const int src = __ffs(hit) - 1;
+            offset = (uint32_t)src;
+            return __shfl_sync(0xffffffffu, t, src);
+        }
+    }
+    const long long pend = ps + (long long)len - 21;                        // positions with >= 22 bits left
+    long long pbeg = ps + 21;
+    if (from > pbeg) { pbeg = from; }
+    for (long long pb = pbeg; pb < pend; pb += 32) {
+        const long long pos = pb + lane;
+        int t = -1;
+        if (pos < pend) { t = match_train_seq(load64(rowp, pos), (uint32_t)(ps + len - pos), mask); }
+        const unsigned hit = __ballot_sync(0xffffffffu, t >= 0);
+        if (hit) {
+            const int src = __ffs(hit) - 1;
+            offset = (uint32_t)(pb + src - ps);
+            return __shfl_sync(0xffffffffu, t, src);
+        }
+    }
+    return -1;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// detect: src/main.cpp:385-414.  New bit j completes a sequence iff D[j .. j+len) == seq, D = the previous 44 bits
+// followed by the new bits.  Positions j >= 44 have their window inside the new bits: 32 of them per thread.
+// ---------------------------------------------------------------------------------------------------
+template <int LEN>
+__device__ __forceinline__ uint32_t match32(uint32_t a0, uint32_t a1, uint32_t a2, unsigned long long seq) {
+    uint32_t m = 0xffffffffu;
+#pragma unroll 1
+    for (int i = 0; i < LEN && m; ++i) {
+        const uint32_t v = (i < 32) ? __funnelshift_l(a1, a0, i) : __funnelshift_l(a2, a1, i - 32);
+        m &= ((seq >> (LEN - 1 - i)) & 1ull) ? v : ~v;
+    }
+    return m;
+}
+
+__global__ void __launch_bounds__(256) bsync_detect_kernel(const BsyncParams p) {
+    const int c = blockIdx.y;
+    const long long n = (long long)units_of(p, c) * p.bits_per_unit;
+    const int cl = (int)p.states[c].bits_in_buf;
+    const uint32_t* __restrict__ rowp = p.wb + (long long)c * p.wstride;
+    if (blockIdx.x == 0 && threadIdx.x < 44 && (int)threadIdx.x < n) {
+        // window overlaps the carried 44-bit history: one position per thread, bit by bit
+        const int j = threadIdx.x;
+        const unsigned long long hist = ((unsigned long long)p.states[c].ts_window_hi << 32) | p.states[c].ts_window_lo;
+        const unsigned long long fresh = load64(rowp, cl);
+        unsigned long long w = 0;                                          // D[j .. j+45), first bit in bit 44; D[j+44] is new bit j
+        for (int i = 0; i < 45; ++i) {
+            const int d = j + i;
+            const unsigned long long b = d < 44 ? (hist >> (43 - d)) & 1ull : (fresh >> (63 - (d - 44))) & 1ull;
+            w = (w << 1) | b;
+        }
+        const bool hit = (w >> 23) == kSeqN || (w >> 23) == kSeqP || (w >> 23) == kSeqQ || (w >> 12) == kSeqNN || (w >> 12) == kSeqPP ||
+                         (w >> 15) == kSeqX || w == kSeqXX || (w >> 7) == kSeqY;
+        if (hit) { atomicMax(&p.last_hit[c], j + 1); }
+    }
+    // bulk: thread handles j = 44 + 32*idx + (0..31); window start in the row = cl + j - 44
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long j0 = 44 + 32 * idx;
+    if (j0 >= n) { return; }
+    const long long L0 = (long long)cl + 32 * idx;
+    const long long wi = L0 >> 5;
+    const int sh = (int)(L0 & 31);
+    const uint32_t w0 = rowp[wi], w1 = rowp[wi + 1], w2 = rowp[wi + 2], w3 = rowp[wi + 3];
+    const uint32_t a0 = __funnelshift_l(w1, w0, sh), a1 = __funnelshift_l(w2, w1, sh), a2 = __funnelshift_l(w3, w2, sh);
+    // bit (31 - q) of m <-> position j0 + q.  Bits past the end of the row are zero, but a position whose bit j does
+    // not exist yet must not count: mask them off (a window needs all of its 45 positions' first `len` bits, and the
+    // last of those is at most bit j itself, so j < n is the whole condition).
+    uint32_t m = match32<22>(a0, a1, a2, kSeqN) | match32<22>(a0, a1, a2, kSeqP) | match32<22>(a0, a1, a2, kSeqQ) |
+                 match32<33>(a0, a1, a2, kSeqNN) | match32<33>(a0, a1, a2, kSeqPP) | match32<30>(a0, a1, a2, kSeqX) |
+                 match32<45>(a0, a1, a2, kSeqXX) | match32<38>(a0, a1, a2, kSeqY);
+    const long long left = n - j0;                                          // valid positions in this word
+    if (left < 32) { m &= ~(0xffffffffu >> left); }
+    if (m) {
+        const int q = 31 - (__ffs(m) - 1);                                  // the LAST matching position of the word
+        atomicMax(&p.last_hit[c], (int)(j0 + q) + 1);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// sync: one warp per channel replays tetra_burst_sync_in call by call.
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t spread4(uint32_t nib) {                  // 4 bits (first = bit 3) -> 4 bytes (first = byte 0)
+    return ((nib >> 3) & 1u) | (((nib >> 2) & 1u) << 8) | (((nib >> 1) & 1u) << 16) | ((nib & 1u) << 24);
+}
+
+__global__ void __launch_bounds__(128) bsync_fsm_kernel(const BsyncParams p) {
+    const int lane = threadIdx.x & 31;
+    const int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (c >= p.n_channels) { return; }
+    tdm_bsync_state* __restrict__ sp = p.states + c;
+    const uint32_t* __restrict__ rowp = p.wb + (long long)c * p.wstride;
+    const uint32_t n = (uint32_t)units_of(p, c) * (uint32_t)p.bits_per_unit;
+    int state = sp->state;
+    uint32_t bib = sp->bits_in_buf;
+    const uint32_t cl0 = bib;
+    const uint32_t base = sp->bitbuf_start_bitnum;                          // row position 0 <-> this stream position
+    uint32_t start = base;
+    uint32_t nfs = sp->next_frame_start_bitnum;
+    uint32_t tn = sp->tn, fn = sp->fn, mn = sp->mn;
+    uint32_t cursor = sp->searched_upto;
+    if ((int32_t)(cursor - base) < 0) { cursor = base; }
+
+    if (p.detect_ts && lane == 0) {
+        // finish the detector: expiry counter and the newest 44 bits (src/main.cpp:403-412)
+        uint32_t found = sp->ts_found, expire = sp->ts_expire;
+        const int last = p.last_hit[c];
+        if (last > 0) {
+            const long long e = 2048LL - ((long long)n - (last - 1));
+            if (e > 0) { found = 1; expire = (uint32_t)e; } else { found = 0; expire = 0; }
+        } else if (expire > 0) {
+            if (expire <= n) { found = 0; expire = 0; } else { expire -= n; }
+        }
+        unsigned long long hist = ((unsigned long long)sp->ts_window_hi << 32) | sp->ts_window_lo;
+        if (n >= 44) { hist = load64(rowp, (long long)cl0 + n - 44) >> 20; }
+        else if (n > 0) { hist = ((hist << n) | (load64(rowp, cl0) >> (64 - n))) & ((1ull << 44) - 1ull); }
+        sp->ts_found = found; sp->ts_expire = expire;
+        sp->ts_window_lo = (uint32_t)hist; sp->ts_window_hi = (uint32_t)(hist >> 32);
+    }
+
+    uint32_t nb = 0, call = 0;
+    const uint32_t call_bits = (uint32_t)p.call_bits;
+    for (uint32_t off = 0; off < n; off += call_bits, ++call) {
+        const uint32_t len = n - off < call_bits ? n - off : call_bits;
+        const uint32_t space = TDM_BSYNC_BITBUF - bib;
+        if (space < len) { const uint32_t delta = len - space; bib -= delta; start += delta; }   // make_bitbuf_space
+        bib += len;
+        const long long ps = (long long)(start - base);
+        uint32_t offs = 0;
+        if (state == TDM_RX_S_UNLOCKED) {
+            if (bib < 2 * TDM_BITS_PER_TS) { continue; }
+            if ((int32_t)(cursor - start) < 0) { cursor = start; }
+            const int rc = warp_find_train_seq(rowp, ps, bib, 1u << TDM_TRAIN_SYNC, (long long)(cursor - base), offs);
+            if (rc < 0) {
+                cursor = start + bib - 37;           // positions up to end - 38 had all 38 bits and did not hold y
+                continue;
+            }
+            state = TDM_RX_S_KNOW_FSTART;
+            nfs = start + offs + 296;
+            continue;
+        }
+        if (state == TDM_RX_S_KNOW_FSTART) {
+            if (start + bib < nfs) { continue; }
+            uint32_t shift = nfs - start;
+            if ((int32_t)shift < 0) { shift = 0; }   // undefined in the reference; see tdm_burst_b200.h
+            bib -= shift; start += shift;
+            nfs += TDM_BITS_PER_TS;
+            state = TDM_RX_S_LOCKED;                 // falls through into the LOCKED case, like the reference
+        }
+        if (bib < TDM_BITS_PER_TS) { continue; }
+        tn += 1;                                     // tetra_tdma_time_add_tn(&time, 1)
+        if (tn > 4) { const uint32_t d = tn / 4; tn %= 4; fn += d; }
+        if (fn > 18) { const uint32_t d = fn / 18; fn %= 18; mn += d; }
+        if (mn > 60) { mn %= 60; }
+        const long long ps2 = (long long)(start - base);
+        const int rc = warp_find_train_seq(rowp, ps2, bib, (1u << TDM_TRAIN_NORM_1) | (1u << TDM_TRAIN_NORM_2) | (1u << TDM_TRAIN_SYNC),
+                                           ps2, offs);
+        bool deliver = false;
+        if (rc == TDM_TRAIN_SYNC) {
+            if (offs == 214) { deliver = true; } else { state = TDM_RX_S_UNLOCKED; cursor = start + TDM_BITS_PER_TS; }
+        } else if (rc == TDM_TRAIN_NORM_1 || rc == TDM_TRAIN_NORM_2) {
+            deliver = (offs == 244);
+        } else {
+            state = TDM_RX_S_UNLOCKED; cursor = start + TDM_BITS_PER_TS;
+        }
+        if (deliver) {
+            if (nb < (uint32_t)p.max_bursts && p.bursts) {
+                tdm_burst* b = p.bursts + ((long long)c * p.max_bursts + nb);
+                if (lane == 0) {
+                    b->bitnum = start; b->train_seq = rc; b->tn = tn; b->fn = fn; b->mn = mn; b->call_index = call;
+                    b->reserved[0] = 0; b->reserved[1] = 0;
+                }
+                uint32_t v = (uint32_t)(load64(rowp, ps2 + 16 * lane) >> 48);       // burst bits 16*lane ..
+                if (lane == 31) { v &= 0xfffcu; }                                   // 510, 511 do not exist
+                reinterpret_cast<uint4*>(b->bits)[lane] = make_uint4(spread4(v >> 12), spread4((v >> 8) & 15u), spread4((v >> 4) & 15u), spread4(v & 15u));
+            }
+            ++nb;
+        }
+        bib -= TDM_BITS_PER_TS; start += TDM_BITS_PER_TS; nfs += TDM_BITS_PER_TS;
+    }
+
+    // carry the buffered bits [start, start + bib) to the front of the state's packed buffer
+    {
+        const long long ps = (long long)(start - base);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const uint32_t w = 4 * lane + k;
+            uint32_t v = 0;
+            if (32 * w < bib) {
+                v = (uint32_t)(load64(rowp, ps + 32 * w) >> 32);
+                const uint32_t left = bib - 32 * w;
+                if (left < 32) { v &= ~(0xffffffffu >> left); }
+            }
+            sp->bitbuf[w] = v;
+        }
+    }
+    if (lane == 0) {
+        sp->state = state; sp->bits_in_buf = bib; sp->bitbuf_start_bitnum = start; sp->next_frame_start_bitnum = nfs;
+        sp->tn = tn; sp->fn = fn; sp->mn = mn; sp->searched_upto = cursor;
+        sp->n_bits += n; sp->n_bursts += nb;
+        if (p.n_bursts) { p.n_bursts[c] = (int)nb; }
+    }
+}
+
+__global__ void __launch_bounds__(128) bsync_find_kernel(const BsyncParams p) {
+    const int lane = threadIdx.x & 31;
+    const int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (c >= p.n_channels) { return; }
+    uint32_t offs = 0;
+    const int rc = warp_find_train_seq(p.wb + (long long)c * p.wstride, 0, p.find_end, p.find_mask, 0, offs);
+    if (lane == 0) { p.find_type[c] = rc; p.find_offset[c] = rc >= 0 ? offs : 0u; }
+}
+
+long long words_for(long long bits) { return (bits + 31) / 32 + kPadWords; }
+
+}  // namespace
+
+struct tdm_bsync {
+    int device = 0;
+    int n_channels = 0;
+    long long max_units = 0;
+    long long wstride = 0;
+    cudaStream_t own_stream = nullptr, stream = nullptr;
+    long long launches = 0;
+    tdm_bsync_state* d_states = nullptr;
+    uint32_t* d_wb = nullptr;
+    int* d_last_hit = nullptr;
+    // staging for TDM_MEM_HOST callers
+    uint8_t* d_in = nullptr;
+    int* d_units = nullptr;
+    int* d_nbursts = nullptr;
+    tdm_burst* d_bursts = nullptr;
+    int d_bursts_cap = 0;
+    cudaEvent_t ev[4] = {};             // around pack / detect / sync of the most recent tdm_bsync_in
+    bool ev_detect = false;
+};
+
+#define BS_CUDA(expr)                                                                                  \
+    do {                                                                                               \
+        cudaError_t e__ = (expr);                                                                      \
+        if (e__ != cudaSuccess) { return tdm_internal_fail(TDM_ERR_CUDA, "%s: %s", #expr, cudaGetErrorString(e__)); } \
+    } while (0)
+
+namespace {
+struct DevGuard {
+    int prev = -1;
+    explicit DevGuard(int dev) { cudaGetDevice(&prev); if (prev != dev) { cudaSetDevice(dev); } else { prev = -1; } }
+    ~DevGuard() { if (prev >= 0) { cudaSetDevice(prev); } }
+};
+
+int check_device(const char* who, int device) {
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) {
+        return tdm_internal_fail(TDM_ERR_NO_DEVICE, "%s: no CUDA device (this library has no CPU fallback)", who);
+    }
+    if (device < 0 || device >= ndev) { return tdm_internal_fail(TDM_ERR_ARG, "%s: device %d out of range (%d devices)", who, device, ndev); }
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess || prop.major != 10) {
+        return tdm_internal_fail(TDM_ERR_NO_DEVICE, "%s: device %d is not sm_100; this library is built for sm_100a only", who, device);
+    }
+    return TDM_OK;
+}
+}  // namespace
+
+extern "C" {
+
+int tdm_bsync_create(int32_t n_channels, int64_t max_units, int32_t device, tdm_bsync** out) {
+    if (!out) { return tdm_internal_fail(TDM_ERR_ARG, "tdm_bsync_create: out is null"); }
+    *out = nullptr;
+    if (n_channels <= 0 || max_units <= 0 || max_units > (1LL << 29)) { return tdm_internal_fail(TDM_ERR_ARG, "tdm_bsync_create: n_channels and max_units must be > 0 (max_units <= 2^29)"); }
+    int rc = check_device("tdm_bsync_create", device);
+    if (rc != TDM_OK) { return rc; }
+    tdm_bsync* h = new (std::nothrow) tdm_bsync();
+    if (!h) { return tdm_internal_fail(TDM_ERR_NOMEM, "tdm_bsync_create: out of host memory"); }
+    h->device = device; h->n_channels = n_channels; h->max_units = max_units;
+    h->wstride = words_for(TDM_BSYNC_BITBUF + 2 * max_units);
+    DevGuard guard(device);
+    auto cleanup = [&](int code) { tdm_bsync_destroy(h); return code; };
+    if (cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking) != cudaSuccess) { return cleanup(tdm_internal_fail(TDM_ERR_CUDA, "cudaStreamCreate failed")); }
+    h->stream = h->own_stream;
+    for (auto& e : h->ev) { if (cudaEventCreate(&e) != cudaSuccess) { return cleanup(tdm_internal_fail(TDM_ERR_CUDA, "cudaEventCreate failed")); } }
+    if (cudaMalloc(&h->d_states, sizeof(tdm_bsync_state) * (size_t)n_channels) != cudaSuccess ||
+        cudaMalloc(&h->d_wb, sizeof(uint32_t) * (size_t)n_channels * (size_t)h->wstride) != cudaSuccess ||
+        cudaMalloc(&h->d_last_hit, sizeof(int) * (size_t)n_channels) != cudaSuccess) {
+        return cleanup(tdm_internal_fail(TDM_ERR_NOMEM, "tdm_bsync_create: cudaMalloc failed"));
+    }
+    rc = tdm_bsync_reset(h);
+    if (rc != TDM_OK) { return cleanup(rc); }
+    *out = h;
+    return TDM_OK;
+}
+
+int tdm_bsync_destroy(tdm_bsync* h) {
+    if (!h) { return TDM_OK; }
+    DevGuard guard(h->device);
+    if (h->own_stream) { cudaStreamSynchronize(h->own_stream); }
+    cudaFree(h->d_states); cudaFree(h->d_wb); cudaFree(h->d_last_hit); cudaFree(h->d_in); cudaFree(h->d_units);
+    cudaFree(h->d_nbursts); cudaFree(h->d_bursts);
+    for (auto& e : h->ev) { if (e) { cudaEventDestroy(e); } }
+    if (h->own_stream) { cudaStreamDestroy(h->own_stream); }
+    delete h;
+    return TDM_OK;
+}
+
+int tdm_bsync_set_stream(tdm_bsync* h, void* cuda_stream) {
+    if (!h) { return tdm_internal_fail(TDM_ERR_ARG, "null handle"); }
+    h->stream = (cuda_stream == TDM_OWN_STREAM) ? h->own_stream : (cudaStream_t)cuda_stream;
+    return TDM_OK;
+}
+
+int tdm_bsync_reset(tdm_bsync* h) {
+    if (!h) { return tdm_internal_fail(TDM_ERR_ARG, "null handle"); }
+    DevGuard guard(h->device);
+    BS_CUDA(cudaMemsetAsync(h->d_states, 0, sizeof(tdm_bsync_state) * (size_t)h->n_channels, h->stream));   // talloc_zero
+    BS_CUDA(cudaStreamSynchronize(h->stream));
+    return TDM_OK;
+}
+
+int tdm_bsync_get_state(tdm_bsync* h, tdm_bsync_state* host_states, int32_t n_channels) {
+    if (!h || !host_states || n_channels != h->n_channels) { return tdm_internal_fail(TDM_ERR_ARG, "tdm_bsync_get_state: bad arguments"); }
+    DevGuard guard(h->device);
+    BS_CUDA(cudaMemcpyAsync(host_states, h->d_states, sizeof(tdm_bsync_state) * (size_t)n_channels, cudaMemcpyDeviceToHost, h->stream));
+    BS_CUDA(cudaStreamSynchronize(h->stream));
+    return TDM_OK;
+}
+
+int tdm_bsync_set_state(tdm_bsync* h, const tdm_bsync_state* host_states, int32_t n_channels) {
+    if (!h || !host_states || n_channels != h->n_channels) { return tdm_internal_fail(TDM_ERR_ARG, "tdm_bsync_set_state: bad arguments"); }
+    for (int c = 0; c < n_channels; ++c) {
+        if (host_states[c].bits_in_buf > TDM_BSYNC_BITBUF || host_states[c].state < 0 || host_states[c].state > TDM_RX_S_LOCKED) {
+            return tdm_internal_fail(TDM_ERR_ARG, "tdm_bsync_set_state: channel %d holds an impossible state", c);
+        }
+    }
+    DevGuard guard(h->device);
+    BS_CUDA(cudaMemcpyAsync(h->d_states, host_states, sizeof(tdm_bsync_state) * (size_t)n_channels, cudaMemcpyHostToDevice, h->stream));
+    BS_CUDA(cudaStreamSynchronize(h->stream));
+    return TDM_OK;
+}
+
+int64_t tdm_bsync_launch_count(const tdm_bsync* h) { return h ? h->launches : 0; }
+
+int tdm_bsync_last_kernel_ms(tdm_bsync* h, float* ms3) {
+    if (!h || !ms3) { return tdm_internal_fail(TDM_ERR_ARG, "tdm_bsync_last_kernel_ms: null argument"); }
+    if (h->launches == 0) { return tdm_internal_fail(TDM_ERR_ARG, "tdm_bsync_last_kernel_ms: nothing launched yet"); }
+    DevGuard guard(h->device);
+    BS_CUDA(cudaEventSynchronize(h->ev[3]));
+    BS_CUDA(cudaEventElapsedTime(&ms3[0], h->ev[0], h->ev[1]));
+    ms3[1] = 0.f;
+    if (h->ev_detect) { BS_CUDA(cudaEventElapsedTime(&ms3[1], h->ev[1], h->ev[2])); }
+    BS_CUDA(cudaEventElapsedTime(&ms3[2], h->ev[2], h->ev[3]));
+    return TDM_OK;
+}
+
+int tdm_bsync_in(tdm_bsync* h, const uint8_t* in, int64_t in_stride, const int32_t* n_units, int32_t units_all,
+                 int32_t in_kind, int32_t call_bits, tdm_burst* bursts, int32_t max_bursts, int32_t* n_bursts,
+                 int32_t detect_ts, int32_t mem_kind) {
+    if (!h) { return tdm_internal_fail(TDM_ERR_ARG, "tdm_bsync_in: null handle"); }
+    if (in_kind != TDM_BSYNC_IN_BITS && in_kind != TDM_BSYNC_IN_DIBITS) { return tdm_internal_fail(TDM_ERR_ARG, "tdm_bsync_in: in_kind"); }
+    if (call_bits < 1 || call_bits > TDM_BSYNC_MAX_CALL_BITS) {
+        return tdm_internal_fail(TDM_ERR_ARG, "tdm_bsync_in: call_bits must be 1..%d (the reference is undefined beyond one slot per call)", TDM_BSYNC_MAX_CALL_BITS);
+    }
+    if (max_bursts < 0 || (max_bursts > 0 && !bursts)) { return tdm_internal_fail(TDM_ERR_ARG, "tdm_bsync_in: bursts"); }
+    if (mem_kind != TDM_MEM_HOST && mem_kind != TDM_MEM_DEVICE) { return tdm_internal_fail(TDM_ERR_ARG, "tdm_bsync_in: mem_kind"); }
+    const int C = h->n_channels;
+    long long umax = units_all;
+    if (n_units && mem_kind == TDM_MEM_HOST) {
+        umax = 0;
+        for (int c = 0; c < C; ++c) { if (n_units[c] > umax) { umax = n_units[c]; } }
+    } else if (n_units) {
+        umax = h->max_units;                        // per-channel counts live on the device: the grid covers the handle's maximum
+    }
+    if (umax < 0 || umax > h->max_units) { return tdm_internal_fail(TDM_ERR_ARG, "tdm_bsync_in: %lld units per channel > max_units %lld", umax, h->max_units); }
+    // (per-channel counts that live on the device cannot be checked here: the caller guarantees n_units[c] <= in_stride)
+    const bool counts_on_device = n_units && mem_kind == TDM_MEM_DEVICE;
+    if (umax > 0 && (!in || (!counts_on_device && in_stride < umax))) { return tdm_internal_fail(TDM_ERR_ARG, "tdm_bsync_in: input pointer / stride"); }
+    if (mem_kind == TDM_MEM_DEVICE && bursts && (reinterpret_cast<uintptr_t>(bursts) & 15u)) { return tdm_internal_fail(TDM_ERR_ARG, "tdm_bsync_in: bursts must be 16-byte aligned"); }
+    DevGuard guard(h->device);
+
+    BsyncParams p{};
+    p.in_stride = in_stride; p.units_all = units_all; p.bits_per_unit = in_kind == TDM_BSYNC_IN_DIBITS ? 2 : 1;
+    p.max_units = (int)h->max_units;
+    p.n_channels = C; p.states = h->d_states; p.wb = h->d_wb; p.wstride = h->wstride; p.last_hit = h->d_last_hit;
+    p.call_bits = call_bits; p.max_bursts = max_bursts; p.detect_ts = detect_ts ? 1 : 0;
+    if (mem_kind == TDM_MEM_DEVICE) {
+        p.in = in; p.n_units = n_units; p.bursts = bursts; p.n_bursts = n_bursts;
+    } else {
+        if (!h->d_in) { BS_CUDA(cudaMalloc(&h->d_in, (size_t)C * (size_t)h->max_units)); }
+        if (!h->d_units) { BS_CUDA(cudaMalloc(&h->d_units, sizeof(int) * (size_t)C)); }
+        if (!h->d_nbursts) { BS_CUDA(cudaMalloc(&h->d_nbursts, sizeof(int) * (size_t)C)); }
+        if (max_bursts > h->d_bursts_cap) {
+            cudaFree(h->d_bursts); h->d_bursts = nullptr; h->d_bursts_cap = 0;
+            BS_CUDA(cudaMalloc(&h->d_bursts, sizeof(tdm_burst) * (size_t)C * (size_t)max_bursts));
+            h->d_bursts_cap = max_bursts;
+        }
+        if (umax > 0) {
+            BS_CUDA(cudaMemcpy2DAsync(h->d_in, (size_t)h->max_units, in, (size_t)in_stride, (size_t)umax, (size_t)C, cudaMemcpyHostToDevice, h->stream));
+        }
+        if (n_units) { BS_CUDA(cudaMemcpyAsync(h->d_units, n_units, sizeof(int) * (size_t)C, cudaMemcpyHostToDevice, h->stream)); }
+        p.in = h->d_in; p.in_stride = h->max_units; p.n_units = n_units ? h->d_units : nullptr;
+        p.bursts = h->d_bursts; p.n_bursts = h->d_nbursts;
+    }
+    const long long row_bits = TDM_BSYNC_BITBUF + umax * p.bits_per_unit + 32 * kPadWords;
+    dim3 gpack((unsigned)((row_bits + kTileBits - 1) / kTileBits), (unsigned)C);
+    cudaEventRecord(h->ev[0], h->stream);
+    bsync_pack_kernel<<<gpack, 256, 0, h->stream>>>(p);
+    h->launches++;
+    cudaEventRecord(h->ev[1], h->stream);
+    h->ev_detect = p.detect_ts != 0;
+    if (p.detect_ts) {
+        const long long words = (umax * p.bits_per_unit + 31) / 32 + 1;
+        dim3 gdet((unsigned)((words + 255) / 256), (unsigned)C);
+        bsync_detect_kernel<<<gdet, 256, 0, h->stream>>>(p);
+        h->launches++;
+    }
+    cudaEventRecord(h->ev[2], h->stream);
+    bsync_fsm_kernel<<<(C + 3) / 4, 128, 0, h->stream>>>(p);
+    h->launches++;
+    cudaEventRecord(h->ev[3], h->stream);
+    BS_CUDA(cudaGetLastError());
+    if (mem_kind == TDM_MEM_HOST) {
+        if (n_bursts) { BS_CUDA(cudaMemcpyAsync(n_bursts, h->d_nbursts, sizeof(int) * (size_t)C, cudaMemcpyDeviceToHost, h->stream)); }
+        if (bursts && max_bursts > 0) {
+            BS_CUDA(cudaMemcpyAsync(bursts, h->d_bursts, sizeof(tdm_burst) * (size_t)C * (size_t)max_bursts, cudaMemcpyDeviceToHost, h->stream));
+        }
+        BS_CUDA(cudaStreamSynchronize(h->stream));
+    }
+    return TDM_OK;
+}
+
+int tdm_find_train_seq(int32_t device, void* cuda_stream, const uint8_t* in, int64_t in_stride, int32_t n_channels,
+                       uint32_t end_of_in, uint32_t mask_of_train_seq, int32_t* out_type, uint32_t* out_offset,
+                       int32_t mem_kind) {
+    if (n_channels <= 0 || !out_type || !out_offset || (end_of_in > 0 && !in) || in_stride < (int64_t)end_of_in || end_of_in > (1u << 30)) {
+        return tdm_internal_fail(TDM_ERR_ARG, "tdm_find_train_seq: bad arguments");
+    }
+    if (mem_kind != TDM_MEM_HOST && mem_kind != TDM_MEM_DEVICE) { return tdm_internal_fail(TDM_ERR_ARG, "tdm_find_train_seq: mem_kind"); }
+    int rc = check_device("tdm_find_train_seq", device);
+    if (rc != TDM_OK) { return rc; }
+    DevGuard guard(device);
+    cudaStream_t stream = (cuda_stream == TDM_OWN_STREAM) ? nullptr : (cudaStream_t)cuda_stream;
+    const size_t C = (size_t)n_channels;
+    const long long wstride = words_for(end_of_in);
+    uint32_t* d_wb = nullptr;
+    uint8_t* d_in = nullptr;
+    int* d_type = nullptr;
+    uint32_t* d_off = nullptr;
+    auto done = [&](int code) { cudaFree(d_wb); cudaFree(d_in); cudaFree(d_type); cudaFree(d_off); return code; };
+    if (cudaMalloc(&d_wb, sizeof(uint32_t) * C * (size_t)wstride) != cudaSuccess) { return done(tdm_internal_fail(TDM_ERR_NOMEM, "tdm_find_train_seq: cudaMalloc failed")); }
+    BsyncParams p{};
+    p.in = in; p.in_stride = in_stride; p.units_all = (int)end_of_in; p.max_units = (int)end_of_in; p.bits_per_unit = 1; p.n_channels = n_channels;
+    p.wb = d_wb; p.wstride = wstride; p.find_end = end_of_in; p.find_mask = mask_of_train_seq;
+    p.find_type = out_type; p.find_offset = out_offset;
+    if (mem_kind == TDM_MEM_HOST) {
+        if (cudaMalloc(&d_in, C * (size_t)(end_of_in ? end_of_in : 1)) != cudaSuccess || cudaMalloc(&d_type, sizeof(int) * C) != cudaSuccess ||
+            cudaMalloc(&d_off, sizeof(uint32_t) * C) != cudaSuccess) {
+            return done(tdm_internal_fail(TDM_ERR_NOMEM, "tdm_find_train_seq: cudaMalloc failed"));
+        }
+        if (end_of_in > 0 && cudaMemcpy2DAsync(d_in, end_of_in, in, (size_t)in_stride, end_of_in, C, cudaMemcpyHostToDevice, stream) != cudaSuccess) {
+            return done(tdm_internal_fail(TDM_ERR_CUDA, "tdm_find_train_seq: copy in failed"));
+        }
+        p.in = d_in; p.in_stride = end_of_in; p.find_type = d_type; p.find_offset = d_off;
+    }
+    const long long row_bits = (long long)end_of_in + 32 * kPadWords;
+    dim3 gpack((unsigned)((row_bits + kTileBits - 1) / kTileBits), (unsigned)n_channels);
+    bsync_pack_kernel<<<gpack, 256, 0, stream>>>(p);
+    bsync_find_kernel<<<(n_channels + 3) / 4, 128, 0, stream>>>(p);
+    if (cudaGetLastError() != cudaSuccess) { return done(tdm_internal_fail(TDM_ERR_CUDA, "tdm_find_train_seq: launch failed")); }
+    if (mem_kind == TDM_MEM_HOST) {
+        cudaMemcpyAsync(out_type, d_type, sizeof(int) * C, cudaMemcpyDeviceToHost, stream);
+        cudaMemcpyAsync(out_offset, d_off, sizeof(uint32_t) * C, cudaMemcpyDeviceToHost, stream);
+    }
+    if (cudaStreamSynchronize(stream) != cudaSuccess) { return done(tdm_internal_fail(TDM_ERR_CUDA, "tdm_find_train_seq: %s", cudaGetErrorString(cudaGetLastError()))); }
+    return done(TDM_OK);
+}
+
+// tetra_burst_rx_cb's block split (phy/tetra_burst.c:33-49,343-393); host only.
+int tdm_burst_demux(const tdm_burst* b, tdm_tp_sap_block* out) {
+    if (!b || !out) { return tdm_internal_fail(TDM_ERR_ARG, "tdm_burst_demux: null argument"); }
+    enum { SB1 = 0, SB2 = 1, NDB = 2, BBK = 3, SCH_F = 5 };       // enum tp_sap_data_type, phy/tetra_burst.h:9-16
+    const uint8_t* u = b->bits;
+    std::memset(out, 0, 3 * sizeof(*out));
+    auto put = [&](int k, int type, int blk, int off, int n, int at = 0) {
+        out[k].type = type; out[k].blk_num = blk; out[k].n_bits = at + n;
+        std::memcpy(out[k].bits + at, u + off, (size_t)n);
+    };
+    switch (b->train_seq) {
+        case TDM_TRAIN_SYNC:                                        // SB1, broadcast block, SB2
+            put(0, SB1, 1, (6 + 1 + 40) * 2, 120); put(1, BBK, 0, (6 + 1 + 40 + 60 + 19) * 2, 30); put(2, SB2, 2, (6 + 1 + 40 + 60 + 19 + 15) * 2, 216);
+            return 3;
+        case TDM_TRAIN_NORM_2:                                      // re-joined broadcast block, two separate blocks
+            put(0, BBK, 0, (5 + 1 + 1 + 108) * 2, 14); put(0, BBK, 0, (5 + 1 + 1 + 108 + 7 + 11) * 2, 16, 14);
+            put(1, NDB, 1, (5 + 1 + 1) * 2, 216); put(2, NDB, 2, (5 + 1 + 1 + 108 + 7 + 11 + 8) * 2, 216);
+            return 3;
+        case TDM_TRAIN_NORM_1:                                      // re-joined broadcast block, both blocks as one SCH/F
+            put(0, BBK, 0, (5 + 1 + 1 + 108) * 2, 14); put(0, BBK, 0, (5 + 1 + 1 + 108 + 7 + 11) * 2, 16, 14);
+            put(1, SCH_F, 0, (5 + 1 + 1) * 2, 216); put(1, SCH_F, 0, (5 + 1 + 1 + 108 + 7 + 11 + 8) * 2, 216, 216);
+            return 2;
+        default:
+            return 0;
+    }
+}
+
+}  // extern "C"

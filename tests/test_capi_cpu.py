@@ -10,8 +10,8 @@ import pytest
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def _header_functions():
-    src = open(os.path.join(ROOT, "include", "tdm_b200.h")).read()
+def _header_functions(name="tdm_b200.h"):
+    src = open(os.path.join(ROOT, "include", name)).read()
     src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
     return sorted(set(re.findall(r"\b(tdm_[a-z0-9_]+)\s*\(", src)))
 
@@ -24,6 +24,11 @@ def test_library_exports_every_declared_symbol(pkg):
         assert hasattr(L, name), f"{name} is declared in include/tdm_b200.h but not exported"
     assert set(declared) == set(pkg.capi.EXPORTED_SYMBOLS)
     assert L.tdm_abi_version() == 1
+    burst = _header_functions("tdm_burst_b200.h")
+    assert set(burst) == set(pkg.capi.EXPORTED_BURST_SYMBOLS), set(burst) ^ set(pkg.capi.EXPORTED_BURST_SYMBOLS)
+    for name in burst:
+        assert hasattr(L, name), f"{name} is declared in include/tdm_burst_b200.h but not exported"
+    assert sorted(os.listdir(os.path.join(ROOT, "include"))) == ["tdm_b200.h", "tdm_burst_b200.h"]
 
 
 def test_library_has_sm100a_code_only(pkg):
@@ -90,3 +95,32 @@ def test_channel_partition():
         assert all(ranges[i][1] == ranges[i + 1][0] for i in range(W - 1))
         sizes = [b - a for a, b in ranges]
         assert max(sizes) - min(sizes) <= 1
+
+
+def test_burst_sync_refuses_without_gpu_and_checks_arguments(pkg):
+    import torch
+    L = pkg.capi.lib()
+    h = C.c_void_p()
+    assert L.tdm_bsync_create(0, 100, 0, C.byref(h)) == pkg.capi.TDM_ERR_ARG
+    assert L.tdm_bsync_create(4, 0, 0, C.byref(h)) == pkg.capi.TDM_ERR_ARG
+    assert L.tdm_bsync_in(None, None, 0, None, 0, 0, 432, None, 0, None, 0, 0) == pkg.capi.TDM_ERR_ARG
+    assert L.tdm_bsync_destroy(None) == pkg.capi.TDM_OK
+    if not torch.cuda.is_available():
+        assert L.tdm_bsync_create(4, 100, 0, C.byref(h)) == pkg.capi.TDM_ERR_NO_DEVICE
+        assert b"no CPU fallback" in L.tdm_last_error()
+
+
+def test_burst_demux_is_host_only_and_matches_the_restatement(pkg):
+    """tdm_burst_demux (no GPU involved) against oracle_bsync.c's split for the three burst types"""
+    from oracle import oracle_bsync as B
+    B.build()
+    rng = np.random.default_rng(4)
+    P = B.PortBsync(1)
+    for typ, bits in [(B.TRAIN_SYNC, B.sync_burst(rng)), (B.TRAIN_NORM_1, B.norm_burst(rng, False)), (B.TRAIN_NORM_2, B.norm_burst(rng, True))]:
+        rec = np.zeros(1, dtype=pkg.capi.BURST_DTYPE)
+        rec["train_seq"] = typ
+        rec["bits"][0, :510] = bits
+        mine, ref = pkg.burst_demux(rec[0]), P.demux(rec[0])
+        assert len(mine) == len(ref) and len(mine) in (2, 3)
+        for f in ["type", "blk_num", "n_bits", "bits"]:
+            assert np.array_equal(mine[f], ref[f]), (typ, f)

@@ -1,0 +1,164 @@
+#!/usr/bin/env python
+"""bench_bsync.py -- throughput of the burst-sync stage (include/tdm_burst_b200.h).
+
+    python tools/bench_bsync.py [--channels 4096] [--symbols 2000000] [--steps 5] [--warmup 3] [--bits] [--detect]
+
+Secondary bench line (the round's headline stays bench.py).  Workload = what the demodulator's bench workload
+leaves in HBM: 4096 channels x 2e6 decoded symbols (one dibit per byte, 8.2 GB), protocol-valid continuous
+downlink streams (a SYNC burst every 4th slot, NORM_1/NORM_2 otherwise, per-channel lead-in, BER 1e-3), fed through
+tetra_burst_sync_in semantics in 432-bit calls.  One step = one tdm_bsync_in over the whole capture, receiver
+state carried from the previous step.
+
+roofline: the pack kernel is the HBM-bound one: algorithmic bytes per decoded bit = 0.5 B read (one dibit byte per
+2 bits; 1 B with --bits) + 1/8 B written.  The sync kernel is a per-channel state machine (latency bound).
+cpu_baseline: the reference's own tetra_burst_sync_in (oracle/_ref, phy/tetra_burst_sync.c compiled unmodified),
+ONE core: its receiver state lives in process globals (t_phy_state, phy/tetra_burst_sync.c:34), so the reference
+cannot run two channels concurrently in one process.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--channels", type=int, default=4096)
+    ap.add_argument("--symbols", type=int, default=2_000_000)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--call-bits", type=int, default=432)
+    ap.add_argument("--bits", action="store_true", help="feed one bit per byte (BitUnpacker output) instead of dibits")
+    ap.add_argument("--detect", action="store_true", help="also run the src/main.cpp:385-414 detector")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+
+    import numpy as np
+    import torch
+    import sdrpp_tetra_demodulator_b200 as pkg
+    from oracle import oracle_bsync as B
+
+    dev = torch.device("cuda", 0)
+    C_, S = args.channels, args.symbols
+    n_bits = 2 * S
+    # ---- capture: 16 distinct protocol-valid base streams of 392 slots (199,920 bits), tiled in time on the device,
+    # each channel with its own lead-in (a cyclic shift of a valid continuous downlink is still one)
+    base_slots = 392
+    bases = np.stack([B.downlink_stream(1000 + k, base_slots, lead_bits=0, ber=1e-3) for k in range(16)])
+    bt = torch.from_numpy(bases).to(dev)
+    reps = -(-n_bits // bases.shape[1]) + 1
+    units = S if not args.bits else n_bits
+    data = torch.empty((C_, units), dtype=torch.uint8, device=dev)
+    g = torch.Generator(device="cpu").manual_seed(5)
+    leads = torch.randint(0, 510, (C_,), generator=g).tolist()
+    for c in range(C_):
+        row = bt[c % 16].repeat(reps)[leads[c]:leads[c] + n_bits]
+        data[c] = row if args.bits else (row[0::2] << 1) | row[1::2]
+    torch.cuda.synchronize()
+
+    max_bursts = n_bits // 510 + 2
+    bs = pkg.BurstSync(C_, units)
+    bs.use_torch_stream()
+    nb = torch.empty(C_, dtype=torch.int32, device=dev)
+    bursts = torch.empty((C_, max_bursts, pkg.capi.BURST_DTYPE.itemsize), dtype=torch.uint8, device=dev)
+
+    def step():
+        bs.feed(data, None, dibits=not args.bits, call_bits=args.call_bits, max_bursts=max_bursts, detect_ts=args.detect, out=(nb, bursts))
+
+    for _ in range(args.warmup):
+        step()
+    torch.cuda.synchronize()
+    l0 = bs.launch_count()
+    kms = np.zeros(3)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for _ in range(args.steps):
+        step()
+        kms += np.array(bs.last_kernel_ms())          # synchronises; per-kernel CUDA events inside the library
+    ev1.record()
+    torch.cuda.synchronize()
+    ms = ev0.elapsed_time(ev1) / args.steps
+    kms /= args.steps
+    launches = bs.launch_count() - l0
+    st = bs.get_state()
+    nbh = nb.cpu().numpy()
+    locked = float((st["state"] == 2).mean())
+    # BER 1e-3 corrupts the training sequence of ~3 % of the slots: those are not delivered (and a corrupted SYNC
+    # sequence costs a re-acquisition), exactly as in the reference
+    assert locked > 0.95 and nbh.min() > 0.8 * (n_bits // 510 - 4), (locked, nbh.min())
+
+    mbits = C_ * n_bits / (ms * 1e-3) / 1e6
+    try:
+        peak = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
+        src = "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        peak, src = 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+    bytes_per_bit = (1.0 if args.bits else 0.5) + 0.125
+    ach = bytes_per_bit * C_ * n_bits / (kms[0] * 1e-3) / 1e9
+
+    # ---- e2e: host buffers through the C ABI (H2D of the decoded stream + D2H of the burst records inside)
+    e2e_ch = min(C_, 256)
+    h_in = torch.empty((e2e_ch, units), dtype=torch.uint8, pin_memory=True)
+    h_in.copy_(data[:e2e_ch])
+    bs2 = pkg.BurstSync(e2e_ch, units)
+    hb = np.zeros((e2e_ch, max_bursts), dtype=pkg.capi.BURST_DTYPE)
+    hn = np.zeros(e2e_ch, dtype=np.int32)
+    hin = h_in.numpy()
+    bs2.feed(hin, None, dibits=not args.bits, call_bits=args.call_bits, max_bursts=max_bursts, out=(hn, hb))
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        bs2.feed(hin, None, dibits=not args.bits, call_bits=args.call_bits, max_bursts=max_bursts, out=(hn, hb))
+    dt = (time.perf_counter() - t0) / args.steps
+    e2e = {"value": round(e2e_ch * n_bits / dt / 1e6, 1), "unit": "Mbits/s", "h2d_bytes_per_step": int(hin.nbytes),
+           "d2h_bytes_per_step": int(hb.nbytes + hn.nbytes), "workload": f"{e2e_ch} channels from pinned host memory via tdm_bsync_in(TDM_MEM_HOST)"}
+
+    cpu = None
+    if not args.no_cpu_baseline:
+        row = data[0].cpu().numpy()
+        bits = row if args.bits else np.stack([(row >> 1) & 1, row & 1], axis=1).reshape(-1).astype(np.uint8)
+        if B.have_ref():
+            R = B.RefBsync(1)
+            t0 = time.perf_counter()
+            reps_cpu = 0
+            while time.perf_counter() - t0 < 10.0:
+                nbr, _, _ = R.feed(bits[None, :], len(bits), args.call_bits, 4)
+                reps_cpu += 1
+            dtc = time.perf_counter() - t0
+            R.close()
+            kind, what = "reference", "reference phy/tetra_burst_sync.c + phy/tetra_burst.c (oracle/_ref, gcc -O2)"
+        else:
+            P = B.PortBsync(1)
+            t0 = time.perf_counter()
+            reps_cpu = 0
+            while time.perf_counter() - t0 < 10.0:
+                nbr, _ = P.feed(bits[None, :], len(bits), args.call_bits, 4)
+                reps_cpu += 1
+            dtc = time.perf_counter() - t0
+            kind, what = "port", "oracle_bsync.c restatement"
+        cpu = {"value": round(reps_cpu * len(bits) / dtc / 1e6, 2), "unit": "Mbits/s", "cores": 1, "kind": kind,
+               "sample": f"1 channel x {len(bits)} bits x {reps_cpu} passes, {what}; single thread (receiver state is process-global in the reference); {dtc:.1f} s"}
+
+    print(json.dumps({
+        "metric": "decoded Mbits/s through burst sync (tetra_burst_sync_in semantics)", "value": round(mbits, 1), "unit": "Mbits/s",
+        "n_gpus": 1, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms, 3), "higher_is_better": True,
+        "dtype": "u8", "data": "synthetic",
+        "config": {"workload": f"{C_} channels x {S} symbols ({'bits' if args.bits else 'dibits'} 1/byte), continuous downlink bursts, BER 1e-3, "
+                               f"{args.call_bits}-bit calls, detector {'on' if args.detect else 'off'}", "l2": "inputs larger than L2",
+                   "locked_channels_frac": locked, "bursts_per_channel_min": int(nbh.min())},
+        "kernel_ms": {"pack": round(float(kms[0]), 3), "detect": round(float(kms[1]), 3), "sync": round(float(kms[2]), 3)},
+        "e2e": e2e, "gpu_launches": int(launches),
+        "roofline": {"bound": "hbm", "kernel": "bsync_pack_kernel", "achieved": round(ach, 1), "peak": peak, "unit": "GB/s",
+                     "frac": round(ach / peak, 4), "traffic": None, "peak_source": src,
+                     "algorithmic_bytes_per_bit": bytes_per_bit},
+        "cpu_baseline": cpu,
+    }))
+
+
+if __name__ == "__main__":
+    main()
