@@ -81,7 +81,10 @@ typedef struct tdm_burst {
     uint32_t tn, fn, mn;                /* t_phy_state.time when the callback ran                          */
     uint32_t call_index;                /* which emulated tetra_burst_sync_in call of this tdm_bsync_in delivered it */
     uint32_t reserved[2];
-    uint8_t  bits[512];                 /* the 510 burst bits, one per byte; [510..511] = 0                */
+    uint32_t bits[16];                  /* the 510 burst bits packed MSB first: bit i = (bits[i/32] >> (31 - i%32)) & 1;
+                                           bits 510 and 511 are 0.  96-byte records: a byte per bit would make the
+                                           burst records the largest stream of the whole stage (1.07 B written per
+                                           input bit against 0.5 B read); tdm_burst_unpack gives the byte form. */
 } tdm_burst;
 
 typedef struct tdm_bsync tdm_bsync;
@@ -136,6 +139,8 @@ typedef struct tdm_tp_sap_block {
     uint8_t bits[432];
 } tdm_tp_sap_block;
 int tdm_burst_demux(const tdm_burst* burst, tdm_tp_sap_block* blocks);
+/* The `burst` argument of tetra_burst_rx_cb: 510 bytes, one bit each.  Host-side helper. */
+int tdm_burst_unpack(const tdm_burst* burst, uint8_t* bits510);
 
 #ifdef __cplusplus
 }

@@ -17,6 +17,16 @@
 
 #include "tdm_burst_b200.h"
 
+/* the checkers keep bursts the way the reference passes them around: one bit per byte */
+typedef struct obs_burst {
+    uint32_t bitnum;
+    int32_t train_seq;
+    uint32_t tn, fn, mn;
+    uint32_t call_index;
+    uint32_t reserved[2];
+    uint8_t bits[512];
+} obs_burst;
+
 /* ETSI EN 300 392-2 9.4.4.3.2-4 training sequences, as the reference tabulates them
  * (phy/tetra_burst.c:61-72, src/main.cpp:457-468). */
 static const uint8_t kSeq_n[22] = { 1,1, 0,1, 0,0, 0,0, 1,1, 1,0, 1,0, 0,1, 1,1, 0,1, 0,0 };
@@ -91,7 +101,7 @@ static void pack_bitbuf(tdm_bsync_state* s, const uint8_t* buf)
 }
 
 /* One channel: n_bits new bits, call_bits per emulated tetra_burst_sync_in call. */
-int obs_in(tdm_bsync_state* s, const uint8_t* bits, uint32_t n_bits, uint32_t call_bits, tdm_burst* bursts, uint32_t max_bursts)
+int obs_in(tdm_bsync_state* s, const uint8_t* bits, uint32_t n_bits, uint32_t call_bits, obs_burst* bursts, uint32_t max_bursts)
 {
     uint8_t buf[TDM_BSYNC_BITBUF + 64];
     uint32_t nb = 0, call = 0;
@@ -145,7 +155,7 @@ int obs_in(tdm_bsync_state* s, const uint8_t* bits, uint32_t n_bits, uint32_t ca
         }
         if (deliver) {
             if (nb < max_bursts) {
-                tdm_burst* b = &bursts[nb];
+                obs_burst* b = &bursts[nb];
                 memset(b, 0, sizeof(*b));
                 b->bitnum = s->bitbuf_start_bitnum; b->train_seq = rc;
                 b->tn = s->tn; b->fn = s->fn; b->mn = s->mn; b->call_index = call;
@@ -192,7 +202,7 @@ void obs_ts_detect(tdm_bsync_state* s, const uint8_t* bits, uint32_t n_bits)
 }
 
 /* tetra_burst_rx_cb's block split (phy/tetra_burst.c:33-49,343-393); DQPSK4_BITS_PER_SYM = 2. */
-int obs_burst_demux(const tdm_burst* b, tdm_tp_sap_block* out)
+int obs_burst_demux(const obs_burst* b, tdm_tp_sap_block* out)
 {
     enum { SB1 = 0, SB2 = 1, NDB = 2, BBK = 3, SCH_F = 5 };
     const uint8_t* u = b->bits;

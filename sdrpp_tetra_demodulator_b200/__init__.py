@@ -4,9 +4,9 @@ cropinghigh/sdrpp-tetra-demodulator's src/dsp.  The product is libtdm_b200.so (h
 sm_100a CUDA behind the C ABI in include/tdm_b200.h); this package is its host-side mirror."""
 from . import capi
 from .capi import TdmConfig, TdmDesign, TdmError, default_config, design_from_config
-from .burst import BurstSync, burst_demux, bursts_view, find_train_seq
+from .burst import BurstSync, burst_demux, bursts_raw, bursts_view, find_train_seq
 from .demod import BitUnpacker, Demodulator, DemodResult, DQPSKSymbolExtractor, PI4DQPSK, synth_capture
 
 __all__ = ["capi", "TdmConfig", "TdmDesign", "TdmError", "default_config", "design_from_config", "Demodulator",
            "DemodResult", "PI4DQPSK", "DQPSKSymbolExtractor", "BitUnpacker", "synth_capture",
-           "BurstSync", "burst_demux", "bursts_view", "find_train_seq"]
+           "BurstSync", "burst_demux", "bursts_raw", "bursts_view", "find_train_seq"]

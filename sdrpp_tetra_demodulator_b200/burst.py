@@ -12,7 +12,7 @@ import numpy as np
 import torch
 
 from . import capi
-from .capi import BURST_DTYPE, BSYNC_STATE_DTYPE, TP_SAP_BLOCK_DTYPE, check, lib
+from .capi import BURST_DTYPE, BURST_UNPACKED_DTYPE, BSYNC_STATE_DTYPE, TP_SAP_BLOCK_DTYPE, check, lib
 
 
 def _ptr(t):
@@ -102,13 +102,25 @@ class BurstSync:
         return int(lib().tdm_bsync_launch_count(self._h))
 
 
-def bursts_view(bursts) -> np.ndarray:
-    """[C][max_bursts] structured view (BURST_DTYPE) of what feed() returned"""
+def bursts_raw(bursts) -> np.ndarray:
+    """[C][max_bursts] structured view (BURST_DTYPE, bits packed) of what feed() returned"""
     if isinstance(bursts, torch.Tensor):
         bursts = bursts.cpu().numpy()
     if bursts.dtype == BURST_DTYPE:
         return bursts
     return np.ascontiguousarray(bursts).view(BURST_DTYPE).reshape(bursts.shape[0], bursts.shape[1])
+
+
+def bursts_view(bursts) -> np.ndarray:
+    """[C][max_bursts] records with the burst one bit per byte (BURST_UNPACKED_DTYPE): the form
+    tetra_burst_rx_cb(burst, 510, type, priv) receives (phy/tetra_burst.c:343)"""
+    raw = bursts_raw(bursts)
+    out = np.zeros(raw.shape, dtype=BURST_UNPACKED_DTYPE)
+    for f in ("bitnum", "train_seq", "tn", "fn", "mn", "call_index"):
+        out[f] = raw[f]
+    be = raw["bits"].astype(">u4")                                   # MSB-first words -> bytes in stream order
+    out["bits"] = np.unpackbits(be.view(np.uint8).reshape(raw.shape + (64,)), axis=-1)
+    return out
 
 
 def find_train_seq(bufs, end_of_in: int, mask: int, device: int = 0):
@@ -131,6 +143,12 @@ def find_train_seq(bufs, end_of_in: int, mask: int, device: int = 0):
 
 def burst_demux(burst: np.ndarray) -> np.ndarray:
     """tetra_burst_rx_cb's split of one burst record into the blocks it passes to tp_sap_udata_ind"""
+    if burst.dtype != BURST_DTYPE:                                   # unpacked record -> the ABI's packed one
+        rec = np.zeros(1, dtype=BURST_DTYPE)
+        for f in ("bitnum", "train_seq", "tn", "fn", "mn", "call_index"):
+            rec[f] = burst[f]
+        rec["bits"][0] = np.packbits(np.asarray(burst["bits"]).reshape(512) & 1).view(">u4").astype(np.uint32)
+        burst = rec[0]
     b = np.ascontiguousarray(burst.reshape(1))
     blocks = np.zeros(3, dtype=TP_SAP_BLOCK_DTYPE)
     n = lib().tdm_burst_demux(b.ctypes.data_as(C.c_void_p), blocks.ctypes.data_as(C.c_void_p))

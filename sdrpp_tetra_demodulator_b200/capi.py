@@ -44,7 +44,7 @@ EXPORTED_SYMBOLS = [
 # ... and include/tdm_burst_b200.h
 EXPORTED_BURST_SYMBOLS = [
     "tdm_bsync_create", "tdm_bsync_destroy", "tdm_bsync_set_stream", "tdm_bsync_reset", "tdm_bsync_in",
-    "tdm_bsync_get_state", "tdm_bsync_set_state", "tdm_bsync_launch_count", "tdm_bsync_last_kernel_ms", "tdm_find_train_seq", "tdm_burst_demux",
+    "tdm_bsync_get_state", "tdm_bsync_set_state", "tdm_bsync_launch_count", "tdm_bsync_last_kernel_ms", "tdm_find_train_seq", "tdm_burst_demux", "tdm_burst_unpack",
 ]
 
 TDM_BITS_PER_TS = 510
@@ -101,7 +101,10 @@ STATE_DTYPE = np.dtype([
 ], align=True)
 # numpy views of tdm_burst / tdm_bsync_state / tdm_tp_sap_block (include/tdm_burst_b200.h)
 BURST_DTYPE = np.dtype([("bitnum", "<u4"), ("train_seq", "<i4"), ("tn", "<u4"), ("fn", "<u4"), ("mn", "<u4"),
-                        ("call_index", "<u4"), ("reserved", "<u4", (2,)), ("bits", "u1", (512,))], align=True)
+                        ("call_index", "<u4"), ("reserved", "<u4", (2,)), ("bits", "<u4", (16,))], align=True)      # 96 bytes, bits packed
+# the same record with the burst one bit per byte (what tetra_burst_rx_cb receives); bursts_view() converts
+BURST_UNPACKED_DTYPE = np.dtype([("bitnum", "<u4"), ("train_seq", "<i4"), ("tn", "<u4"), ("fn", "<u4"), ("mn", "<u4"),
+                                 ("call_index", "<u4"), ("reserved", "<u4", (2,)), ("bits", "u1", (512,))], align=True)
 BSYNC_STATE_DTYPE = np.dtype([("state", "<i4"), ("bits_in_buf", "<u4"), ("bitbuf_start_bitnum", "<u4"),
                               ("next_frame_start_bitnum", "<u4"), ("tn", "<u4"), ("fn", "<u4"), ("mn", "<u4"),
                               ("ts_found", "<u4"), ("ts_expire", "<u4"), ("ts_window_lo", "<u4"), ("ts_window_hi", "<u4"),
@@ -165,6 +168,7 @@ def lib() -> C.CDLL:
         "tdm_bsync_last_kernel_ms": (C.c_int, [vp, C.POINTER(C.c_float)]),
         "tdm_find_train_seq": (C.c_int, [i32, vp, vp, i64, i32, u32, u32, vp, vp, i32]),
         "tdm_burst_demux": (C.c_int, [vp, vp]),
+        "tdm_burst_unpack": (C.c_int, [vp, vp]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)

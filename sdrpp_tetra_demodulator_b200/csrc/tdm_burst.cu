@@ -14,11 +14,13 @@
 //   pack    (HBM bound: reads 1 byte per input unit, writes 1/8 byte per bit)  -- every (channel, 4096-bit tile)
 //           in parallel: 16-byte loads, 16 bytes -> 16 (or 32) bits with one multiply per 4 bytes, re-aligned
 //           through shared memory behind the channel's carried bits;
-//   detect  (optional, bit-parallel) -- every (channel, 32 positions): the eight training sequences are matched
-//           against 32 window positions at once with funnel shifts and AND/ANDN, early exit when no candidate
-//           position is left;
+//   match   (bit-parallel) -- every (channel, 32 positions): "does y / n-or-p start here" for 32 positions at once,
+//           one funnel shift + one LOP3 per sequence bit, fully unrolled; writes two match bitmaps next to the
+//           packed row.  With detect_ts it also matches the other five sequences and keeps the last hit per
+//           channel for the src/main.cpp:385-414 detector;
 //   sync    one warp per channel replays the reference's calls: the state machine is scalar (warp uniform),
-//           every search is 32 positions per step with 64-bit window compares and a ballot.
+//           a search is "first set bit of the match bitmap inside the buffer" (one word per lane + ballot), then
+//           one 64-bit window compare to confirm type and remaining length.
 #include <cuda_runtime.h>
 #include <cstdint>
 #include <cstring>
@@ -30,7 +32,7 @@
 
 namespace {
 
-constexpr int kTileBits = 4096;                 // logical bits per pack CTA
+constexpr int kTileBits = 16384;                // logical bits per pack CTA: 2-4 16-byte loads in flight per thread
 constexpr int kTileWords = kTileBits / 32;
 constexpr int kPadWords = 8;                    // readable words past the last bit of a row (64-bit window loads)
 
@@ -63,6 +65,8 @@ struct BsyncParams {
     int n_channels;
     tdm_bsync_state* states;      // null for the stateless find
     uint32_t* wb;                 // [C][wstride] packed work rows: carried bits then the new bits
+    uint32_t* my;                 // [C][wstride] bit (31 - q) of word w set <=> the SYNC sequence y starts at row position 32 w + q
+    uint32_t* mnp;                // [C][wstride] same for the normal sequences n or p
     long long wstride;
     int* last_hit;                // [C] detector: 1 + index of the last new bit that completed a sequence, 0 = none
     int call_bits;
@@ -89,7 +93,8 @@ __device__ __forceinline__ uint32_t pack4_bits(uint32_t x) { return (((x & 0x010
 __device__ __forceinline__ uint32_t pack4_dibits(uint32_t x) { return (((x & 0x03030303u) * 0x40100401u) >> 24) & 0xffu; }
 
 __global__ void __launch_bounds__(256) bsync_pack_kernel(const BsyncParams p) {
-    __shared__ uint16_t s16[2 * 132 + 8];
+    constexpr int kMaxGroups = kTileBits / 16 + 1;                          // 16 units per group; bits: 1025, dibits: 513
+    __shared__ uint16_t s16[kMaxGroups + 7];
     const int c = blockIdx.y;
     const int bpu = p.bits_per_unit;
     const int nu = units_of(p, c);
@@ -101,34 +106,50 @@ __global__ void __launch_bounds__(256) bsync_pack_kernel(const BsyncParams p) {
     if (tile0 >= total + 32 * kPadWords) { return; }
     const uint8_t* __restrict__ row = p.in + (long long)c * p.in_stride;
     const long long ib0 = tile0 - cl;                                       // first input bit of the tile (may be < 0)
-    long long u0 = ib0 >= 0 ? ib0 / bpu : -((-ib0 + bpu - 1) / bpu);        // floor(ib0 / bpu)
+    const long long u0 = ib0 >= 0 ? ib0 / bpu : -((-ib0 + bpu - 1) / bpu);  // floor(ib0 / bpu)
     const long long A = u0 & ~15LL;                                         // aligned first unit staged
-    const int groups = (bpu == 1) ? 257 : 129;                              // 16 units each
+    const int groups = kTileBits / (16 * bpu) + 1;
     const bool aligned = ((reinterpret_cast<uintptr_t>(row) & 15u) == 0);
-    for (int g = threadIdx.x; g < groups; g += blockDim.x) {
-        const long long ua = A + 16LL * g;
-        uint32_t w[4] = { 0, 0, 0, 0 };
-        if (ua >= 0 && ua + 16 <= nu && aligned) {
-            const uint4 v = __ldg(reinterpret_cast<const uint4*>(row + ua));
-            w[0] = v.x; w[1] = v.y; w[2] = v.z; w[3] = v.w;
-        } else if (ua + 16 > 0 && ua < nu) {
+    constexpr int kPer = (kMaxGroups + 255) / 256;                          // groups per thread: all loads first, then the packing
+    uint32_t w[kPer][4];
 #pragma unroll
-            for (int k = 0; k < 16; ++k) {
-                const long long u = ua + k;
-                const uint32_t b = (u >= 0 && u < nu) ? (uint32_t)row[u] : 0u;
-                w[k >> 2] |= b << (8 * (k & 3));
+    for (int r = 0; r < kPer; ++r) {
+        const int g = threadIdx.x + 256 * r;
+        const long long ua = A + 16LL * g;
+        w[r][0] = w[r][1] = w[r][2] = w[r][3] = 0u;
+        if (g < groups) {
+            if (ua >= 0 && ua + 16 <= nu && aligned) {
+                const uint4 v = __ldg(reinterpret_cast<const uint4*>(row + ua));
+                w[r][0] = v.x; w[r][1] = v.y; w[r][2] = v.z; w[r][3] = v.w;
+            } else if (ua + 16 > 0 && ua < nu) {
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    uint32_t acc = 0;
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const long long u = ua + 4 * q + k;
+                        const uint32_t b = (u >= 0 && u < nu) ? (uint32_t)row[u] : 0u;
+                        acc |= b << (8 * k);
+                    }
+                    w[r][q] = acc;
+                }
             }
         }
-        if (bpu == 1) {
-            s16[g] = (uint16_t)((pack4_bits(w[0]) << 12) | (pack4_bits(w[1]) << 8) | (pack4_bits(w[2]) << 4) | pack4_bits(w[3]));
-        } else {
-            s16[2 * g] = (uint16_t)((pack4_dibits(w[0]) << 8) | pack4_dibits(w[1]));
-            s16[2 * g + 1] = (uint16_t)((pack4_dibits(w[2]) << 8) | pack4_dibits(w[3]));
+    }
+#pragma unroll
+    for (int r = 0; r < kPer; ++r) {
+        const int g = threadIdx.x + 256 * r;
+        if (g < groups) {
+            if (bpu == 1) {
+                s16[g] = (uint16_t)((pack4_bits(w[r][0]) << 12) | (pack4_bits(w[r][1]) << 8) | (pack4_bits(w[r][2]) << 4) | pack4_bits(w[r][3]));
+            } else {
+                s16[2 * g] = (uint16_t)((pack4_dibits(w[r][0]) << 8) | pack4_dibits(w[r][1]));
+                s16[2 * g + 1] = (uint16_t)((pack4_dibits(w[r][2]) << 8) | pack4_dibits(w[r][3]));
+            }
         }
     }
     __syncthreads();
-    if (threadIdx.x < kTileWords) {
-        const int t = threadIdx.x;
+    for (int t = threadIdx.x; t < kTileWords; t += 256) {
         const long long wi = (long long)blockIdx.x * kTileWords + t;
         if (wi * 32 < total + 32 * kPadWords && wi < p.wstride) {
             const int o = (int)(ib0 - A * bpu) + 32 * t;                    // bit offset into the staged bits
@@ -150,6 +171,53 @@ __device__ __forceinline__ unsigned long long load64(const uint32_t* __restrict_
     return ((unsigned long long)hi << 32) | lo;
 }
 
+// A warp's window onto its packed row.  The sync kernel replays thousands of calls per channel and every call
+// searches a few hundred bits right behind the previous call's: reading them from global memory made each of
+// the ~8 search steps of a call wait for DRAM (5200 cycles per call measured).  The window is a shared-memory
+// copy of kWinWords consecutive row words, refilled with coalesced loads only when a search leaves it
+// (about every 11th call while locked).  With cache == nullptr it reads the row directly (stateless find).
+constexpr int kWinWords = 192;                  // 6144 bits >= the 4096-bit buffer + look-ahead
+struct RowWindow {
+    const uint32_t* __restrict__ rowp;          // packed bits
+    const uint32_t* __restrict__ myp;           // match bitmaps (null for the stateless find)
+    const uint32_t* __restrict__ mnpp;
+    uint32_t* cache;                            // [3][kWinWords] shared memory of this warp (bits, my, mnp), or null
+    long long cbase;                            // row word index of cache[0]; -1 = empty
+    long long wstride;
+
+    // make bits [pos, pos + nbits + 64) (and their bitmap words) readable
+    __device__ __forceinline__ void ensure(long long pos, uint32_t nbits) {
+        if (!cache) { return; }
+        const long long w0 = pos >> 5, w1 = ((pos + nbits + 63) >> 5) + 2;
+        if (cbase >= 0 && w0 >= cbase && w1 <= cbase + kWinWords) { return; }
+        const int lane = threadIdx.x & 31;
+        cbase = w0;
+        __syncwarp();
+#pragma unroll
+        for (int k = 0; k < kWinWords / 32; ++k) {
+            const long long wi = cbase + 32 * k + lane;
+            const bool in = wi < wstride;
+            cache[32 * k + lane] = in ? rowp[wi] : 0u;
+            cache[kWinWords + 32 * k + lane] = in ? myp[wi] : 0u;
+            cache[2 * kWinWords + 32 * k + lane] = in ? mnpp[wi] : 0u;
+        }
+        __syncwarp();
+    }
+    __device__ __forceinline__ unsigned long long get64(long long pos) const {
+        if (!cache) { return load64(rowp, pos); }
+        const int wi = (int)((pos >> 5) - cbase);
+        const int sh = (int)(pos & 31);
+        const uint32_t w0 = cache[wi], w1 = cache[wi + 1], w2 = cache[wi + 2];
+        const uint32_t hi = __funnelshift_l(w1, w0, sh), lo = __funnelshift_l(w2, w1, sh);
+        return ((unsigned long long)hi << 32) | lo;
+    }
+    // match-bitmap word wi of the row (absolute word index inside the window)
+    __device__ __forceinline__ uint32_t mword(long long wi, bool with_np) const {
+        const int k = (int)(wi - cbase);
+        return cache[kWinWords + k] | (with_np ? cache[2 * kWinWords + k] : 0u);
+    }
+};
+
 // which enabled sequence starts at a window W with `rem` bits left in the buffer; -1 = none.
 // Order of the tests as in tetra_burst.c:309-338.
 __device__ __forceinline__ int match_train_seq(unsigned long long W, uint32_t rem, uint32_t mask) {
@@ -164,15 +232,16 @@ __device__ __forceinline__ int match_train_seq(unsigned long long W, uint32_t re
 // tetra_find_train_seq over buffer [ps, ps + len) of a packed row, by one warp.  `from` = first position >= ps + 21
 // that still has to be examined with the plain rule (earlier ones are known not to hold an enabled sequence).
 // Returns the type (warp uniform) and the offset relative to ps.
-__device__ __forceinline__ int warp_find_train_seq(const uint32_t* __restrict__ rowp, long long ps, uint32_t len, uint32_t mask,
+__device__ __forceinline__ int warp_find_train_seq(RowWindow& win, long long ps, uint32_t len, uint32_t mask,
                                                    long long from, uint32_t& offset) {
     const int lane = threadIdx.x & 31;
     if (len < 22) { return -1; }
+    win.ensure(ps, len);
     // positions 0..20: the reference's look-ahead register does not hold in[i..i+21] there (one bit short preload,
     // tetra_burst.c:292-300): it holds in[i-1..19] ++ in[21..21+i] (a leading 0 for i = 0); the position is examined
     // only if THAT equals the first 22 bits of y, n, p, q or x.
     {
-        const unsigned long long W0 = load64(rowp, ps);
+        const unsigned long long W0 = win.get64(ps);
         int t = -1;
         if (lane <= 20 && len - (uint32_t)lane >= 22) {
             const int i = lane;
@@ -180,7 +249,7 @@ __device__ __forceinline__ int warp_find_train_seq(const uint32_t* __restrict__ 
             const uint32_t part2 = (uint32_t)(W0 >> (42 - i)) & ((1u << (i + 1)) - 1u);
             const uint32_t f = (part1 << (i + 1)) | part2;
             const bool pass = f == kPreY || f == (uint32_t)kSeqN || f == (uint32_t)kSeqP || f == (uint32_t)kSeqQ || f == kPreX;
-            if (pass) { t = match_train_seq(load64(rowp, ps + i), len - (uint32_t)i, mask); }
+            if (pass) { t = match_train_seq(win.get64(ps + i), len - (uint32_t)i, mask); }
         }
         const unsigned hit = __ballot_sync(0xffffffffu, t >= 0);
         if (hit) {
@@ -195,7 +264,7 @@ __device__ __forceinline__ int warp_find_train_seq(const uint32_t* __restrict__ 
     for (long long pb = pbeg; pb < pend; pb += 32) {
         const long long pos = pb + lane;
         int t = -1;
-        if (pos < pend) { t = match_train_seq(load64(rowp, pos), (uint32_t)(ps + len - pos), mask); }
+        if (pos < pend) { t = match_train_seq(win.get64(pos), (uint32_t)(ps + len - pos), mask); }
         const unsigned hit = __ballot_sync(0xffffffffu, t >= 0);
         if (hit) {
             const int src = __ffs(hit) - 1;
@@ -207,26 +276,34 @@ __device__ __forceinline__ int warp_find_train_seq(const uint32_t* __restrict__ 
 }
 
 // ---------------------------------------------------------------------------------------------------
-// detect: src/main.cpp:385-414.  New bit j completes a sequence iff D[j .. j+len) == seq, D = the previous 44 bits
-// followed by the new bits.  Positions j >= 44 have their window inside the new bits: 32 of them per thread.
+// match: for every row position, does a training sequence START there (content only; whether it still fits into
+// the buffer is the state machine's business).  32 positions per thread: v_i = the 32 positions' i-th bits is one
+// funnel shift of the aligned row words, and a sequence bit either keeps (AND) or clears (ANDN) candidates; after
+// unrolling, the sequence is a compile-time constant, so each step is one SHF (shared by all sequences) + one LOP3.
+//
+// detect (src/main.cpp:385-414): new bit j completes a sequence iff D[j .. j+len) == seq with D = the previous 44
+// bits followed by the new bits.  For j >= 44 the window starts at row position cl + j - 44, inside the new bits,
+// so the same match words serve; the 44 positions that overlap the carried history are done one per thread.
 // ---------------------------------------------------------------------------------------------------
 template <int LEN>
 __device__ __forceinline__ uint32_t match32(uint32_t a0, uint32_t a1, uint32_t a2, unsigned long long seq) {
     uint32_t m = 0xffffffffu;
-#pragma unroll 1
-    for (int i = 0; i < LEN && m; ++i) {
-        const uint32_t v = (i < 32) ? __funnelshift_l(a1, a0, i) : __funnelshift_l(a2, a1, i - 32);
+#pragma unroll
+    for (int i = 0; i < LEN; ++i) {
+        const uint32_t v = i == 0 ? a0 : (i < 32 ? __funnelshift_l(a1, a0, i) : (i == 32 ? a1 : __funnelshift_l(a2, a1, i - 32)));
         m &= ((seq >> (LEN - 1 - i)) & 1ull) ? v : ~v;
     }
     return m;
 }
 
-__global__ void __launch_bounds__(256) bsync_detect_kernel(const BsyncParams p) {
+template <bool DETECT>
+__global__ void __launch_bounds__(256) bsync_match_kernel(const BsyncParams p) {
     const int c = blockIdx.y;
     const long long n = (long long)units_of(p, c) * p.bits_per_unit;
     const int cl = (int)p.states[c].bits_in_buf;
+    const long long total = cl + n;
     const uint32_t* __restrict__ rowp = p.wb + (long long)c * p.wstride;
-    if (blockIdx.x == 0 && threadIdx.x < 44 && (int)threadIdx.x < n) {
+    if (DETECT && blockIdx.x == 0 && threadIdx.x < 44 && (long long)threadIdx.x < n) {
         // window overlaps the carried 44-bit history: one position per thread, bit by bit
         const int j = threadIdx.x;
         const unsigned long long hist = ((unsigned long long)p.states[c].ts_window_hi << 32) | p.states[c].ts_window_lo;
@@ -241,37 +318,93 @@ __global__ void __launch_bounds__(256) bsync_detect_kernel(const BsyncParams p) 
                          (w >> 15) == kSeqX || w == kSeqXX || (w >> 7) == kSeqY;
         if (hit) { atomicMax(&p.last_hit[c], j + 1); }
     }
-    // bulk: thread handles j = 44 + 32*idx + (0..31); window start in the row = cl + j - 44
-    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const long long j0 = 44 + 32 * idx;
-    if (j0 >= n) { return; }
-    const long long L0 = (long long)cl + 32 * idx;
-    const long long wi = L0 >> 5;
-    const int sh = (int)(L0 & 31);
-    const uint32_t w0 = rowp[wi], w1 = rowp[wi + 1], w2 = rowp[wi + 2], w3 = rowp[wi + 3];
-    const uint32_t a0 = __funnelshift_l(w1, w0, sh), a1 = __funnelshift_l(w2, w1, sh), a2 = __funnelshift_l(w3, w2, sh);
-    // bit (31 - q) of m <-> position j0 + q.  Bits past the end of the row are zero, but a position whose bit j does
-    // not exist yet must not count: mask them off (a window needs all of its 45 positions' first `len` bits, and the
-    // last of those is at most bit j itself, so j < n is the whole condition).
-    uint32_t m = match32<22>(a0, a1, a2, kSeqN) | match32<22>(a0, a1, a2, kSeqP) | match32<22>(a0, a1, a2, kSeqQ) |
-                 match32<33>(a0, a1, a2, kSeqNN) | match32<33>(a0, a1, a2, kSeqPP) | match32<30>(a0, a1, a2, kSeqX) |
-                 match32<45>(a0, a1, a2, kSeqXX) | match32<38>(a0, a1, a2, kSeqY);
-    const long long left = n - j0;                                          // valid positions in this word
-    if (left < 32) { m &= ~(0xffffffffu >> left); }
-    if (m) {
-        const int q = 31 - (__ffs(m) - 1);                                  // the LAST matching position of the word
-        atomicMax(&p.last_hit[c], (int)(j0 + q) + 1);
+    const long long wi = (long long)blockIdx.x * blockDim.x + threadIdx.x;     // positions 32 wi .. 32 wi + 31
+    if (wi * 32 >= total || wi + 2 >= p.wstride) { return; }
+    const uint32_t a0 = rowp[wi], a1 = rowp[wi + 1], a2 = rowp[wi + 2];
+    const uint32_t my = match32<38>(a0, a1, a2, kSeqY);
+    const uint32_t mnp = match32<22>(a0, a1, a2, kSeqN) | match32<22>(a0, a1, a2, kSeqP);
+    p.my[(long long)c * p.wstride + wi] = my;
+    p.mnp[(long long)c * p.wstride + wi] = mnp;
+    if (DETECT) {
+        uint32_t m = my | mnp | match32<22>(a0, a1, a2, kSeqQ) | match32<33>(a0, a1, a2, kSeqNN) | match32<33>(a0, a1, a2, kSeqPP) |
+                     match32<30>(a0, a1, a2, kSeqX) | match32<45>(a0, a1, a2, kSeqXX);
+        // window start L = 32 wi + q completes at new bit j = L - cl + 44: it counts iff L >= cl and j < n
+        const long long lo = cl, hi = total - 44;                          // valid L in [lo, hi)
+        const long long L0 = wi * 32;
+        if (L0 + 32 <= lo || L0 >= hi) { m = 0; }
+        else {
+            if (L0 < lo) { m &= 0xffffffffu >> (int)(lo - L0); }
+            if (L0 + 32 > hi) { m &= ~(0xffffffffu >> (int)(hi - L0)); }
+        }
+        if (m) {
+            const int q = 31 - (__ffs(m) - 1);                              // the LAST matching position of the word
+            atomicMax(&p.last_hit[c], (int)(L0 + q - cl + 44) + 1);
+        }
     }
+}
+
+// The state machine's search: tetra_find_train_seq over buffer [ps, ps + len) with mask {SYNC} (with_np = false) or
+// {NORM_1, NORM_2, SYNC}, driven by the match bitmaps.  `from` as in warp_find_train_seq.
+__device__ __forceinline__ int warp_find_bitmap(RowWindow& win, long long ps, uint32_t len, bool with_np, long long from, uint32_t& offset) {
+    const int lane = threadIdx.x & 31;
+    if (len < 22) { return -1; }
+    win.ensure(ps, len);
+    const uint32_t mask = with_np ? ((1u << TDM_TRAIN_NORM_1) | (1u << TDM_TRAIN_NORM_2) | (1u << TDM_TRAIN_SYNC)) : (1u << TDM_TRAIN_SYNC);
+    // positions 0..20 (look-ahead quirk, see warp_find_train_seq): only worth a look if a sequence starts there at all
+    {
+        const long long w0 = ps >> 5;
+        const int sh = (int)(ps & 31);
+        const uint32_t head = __funnelshift_l(win.mword(w0 + 1, with_np), win.mword(w0, with_np), sh) >> 11;    // positions ps .. ps+20
+        if (head) {
+            const unsigned long long W0 = win.get64(ps);
+            int t = -1;
+            if (lane <= 20 && len - (uint32_t)lane >= 22) {
+                const int i = lane;
+                const uint32_t part1 = (uint32_t)(W0 >> 44) & ((1u << (21 - i)) - 1u);
+                const uint32_t part2 = (uint32_t)(W0 >> (42 - i)) & ((1u << (i + 1)) - 1u);
+                const uint32_t f = (part1 << (i + 1)) | part2;
+                const bool pass = f == kPreY || f == (uint32_t)kSeqN || f == (uint32_t)kSeqP || f == (uint32_t)kSeqQ || f == kPreX;
+                if (pass) { t = match_train_seq(win.get64(ps + i), len - (uint32_t)i, mask); }
+            }
+            const unsigned hit = __ballot_sync(0xffffffffu, t >= 0);
+            if (hit) {
+                const int src = __ffs(hit) - 1;
+                offset = (uint32_t)src;
+                return __shfl_sync(0xffffffffu, t, src);
+            }
+        }
+    }
+    long long lo = ps + 21;
+    if (from > lo) { lo = from; }
+    const long long hi = ps + (long long)len - 21;                          // positions with >= 22 bits left
+    for (long long wbase = lo >> 5; wbase * 32 < hi; wbase += 32) {
+        const long long wi = wbase + lane;
+        const long long L0 = wi * 32;
+        uint32_t m = 0;
+        if (L0 < hi && L0 + 32 > lo) {
+            m = win.mword(wi, with_np);
+            if (L0 < lo) { m &= 0xffffffffu >> (int)(lo - L0); }
+            if (L0 + 32 > hi) { m &= ~(0xffffffffu >> (int)(hi - L0)); }
+        }
+        for (;;) {
+            const unsigned cand = __ballot_sync(0xffffffffu, m != 0u);
+            if (!cand) { break; }
+            const int src = __ffs(cand) - 1;
+            const int q = __clz(__shfl_sync(0xffffffffu, m, src));          // earliest position = most significant set bit
+            const long long pos = (wbase + src) * 32 + q;
+            const int t = match_train_seq(win.get64(pos), (uint32_t)(ps + len - pos), mask);
+            if (t >= 0) { offset = (uint32_t)(pos - ps); return t; }
+            if (lane == src) { m &= ~(0x80000000u >> q); }                  // y with fewer than 38 bits left: not a match yet
+        }
+    }
+    return -1;
 }
 
 // ---------------------------------------------------------------------------------------------------
 // sync: one warp per channel replays tetra_burst_sync_in call by call.
 // ---------------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t spread4(uint32_t nib) {                  // 4 bits (first = bit 3) -> 4 bytes (first = byte 0)
-    return ((nib >> 3) & 1u) | (((nib >> 2) & 1u) << 8) | (((nib >> 1) & 1u) << 16) | ((nib & 1u) << 24);
-}
-
 __global__ void __launch_bounds__(128) bsync_fsm_kernel(const BsyncParams p) {
+    __shared__ uint32_t win_s[4][3 * kWinWords];
     const int lane = threadIdx.x & 31;
     const int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (c >= p.n_channels) { return; }
@@ -287,6 +420,7 @@ __global__ void __launch_bounds__(128) bsync_fsm_kernel(const BsyncParams p) {
     uint32_t tn = sp->tn, fn = sp->fn, mn = sp->mn;
     uint32_t cursor = sp->searched_upto;
     if ((int32_t)(cursor - base) < 0) { cursor = base; }
+    RowWindow win{ rowp, p.my + (long long)c * p.wstride, p.mnp + (long long)c * p.wstride, win_s[threadIdx.x >> 5], -1, p.wstride };
 
     if (p.detect_ts && lane == 0) {
         // finish the detector: expiry counter and the newest 44 bits (src/main.cpp:403-412)
@@ -317,7 +451,7 @@ __global__ void __launch_bounds__(128) bsync_fsm_kernel(const BsyncParams p) {
         if (state == TDM_RX_S_UNLOCKED) {
             if (bib < 2 * TDM_BITS_PER_TS) { continue; }
             if ((int32_t)(cursor - start) < 0) { cursor = start; }
-            const int rc = warp_find_train_seq(rowp, ps, bib, 1u << TDM_TRAIN_SYNC, (long long)(cursor - base), offs);
+            const int rc = warp_find_bitmap(win, ps, bib, false, (long long)(cursor - base), offs);
             if (rc < 0) {
                 cursor = start + bib - 37;           // positions up to end - 38 had all 38 bits and did not hold y
                 continue;
@@ -340,8 +474,7 @@ __global__ void __launch_bounds__(128) bsync_fsm_kernel(const BsyncParams p) {
         if (fn > 18) { const uint32_t d = fn / 18; fn %= 18; mn += d; }
         if (mn > 60) { mn %= 60; }
         const long long ps2 = (long long)(start - base);
-        const int rc = warp_find_train_seq(rowp, ps2, bib, (1u << TDM_TRAIN_NORM_1) | (1u << TDM_TRAIN_NORM_2) | (1u << TDM_TRAIN_SYNC),
-                                           ps2, offs);
+        const int rc = warp_find_bitmap(win, ps2, bib, true, ps2, offs);
         bool deliver = false;
         if (rc == TDM_TRAIN_SYNC) {
             if (offs == 214) { deliver = true; } else { state = TDM_RX_S_UNLOCKED; cursor = start + TDM_BITS_PER_TS; }
@@ -353,13 +486,15 @@ __global__ void __launch_bounds__(128) bsync_fsm_kernel(const BsyncParams p) {
         if (deliver) {
             if (nb < (uint32_t)p.max_bursts && p.bursts) {
                 tdm_burst* b = p.bursts + ((long long)c * p.max_bursts + nb);
-                if (lane == 0) {
+                if (lane == 16) {
                     b->bitnum = start; b->train_seq = rc; b->tn = tn; b->fn = fn; b->mn = mn; b->call_index = call;
                     b->reserved[0] = 0; b->reserved[1] = 0;
                 }
-                uint32_t v = (uint32_t)(load64(rowp, ps2 + 16 * lane) >> 48);       // burst bits 16*lane ..
-                if (lane == 31) { v &= 0xfffcu; }                                   // 510, 511 do not exist
-                reinterpret_cast<uint4*>(b->bits)[lane] = make_uint4(spread4(v >> 12), spread4((v >> 8) & 15u), spread4((v >> 4) & 15u), spread4(v & 15u));
+                if (lane < 16) {                                                    // the burst is already packed: 16 words
+                    uint32_t v = (uint32_t)(win.get64(ps2 + 32 * lane) >> 32);
+                    if (lane == 15) { v &= 0xfffffffcu; }                           // bits 510, 511 do not exist
+                    b->bits[lane] = v;
+                }
             }
             ++nb;
         }
@@ -394,7 +529,8 @@ __global__ void __launch_bounds__(128) bsync_find_kernel(const BsyncParams p) {
     const int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (c >= p.n_channels) { return; }
     uint32_t offs = 0;
-    const int rc = warp_find_train_seq(p.wb + (long long)c * p.wstride, 0, p.find_end, p.find_mask, 0, offs);
+    RowWindow win{ p.wb + (long long)c * p.wstride, nullptr, nullptr, nullptr, -1, p.wstride };
+    const int rc = warp_find_train_seq(win, 0, p.find_end, p.find_mask, 0, offs);
     if (lane == 0) { p.find_type[c] = rc; p.find_offset[c] = rc >= 0 ? offs : 0u; }
 }
 
@@ -467,7 +603,7 @@ int tdm_bsync_create(int32_t n_channels, int64_t max_units, int32_t device, tdm_
     h->stream = h->own_stream;
     for (auto& e : h->ev) { if (cudaEventCreate(&e) != cudaSuccess) { return cleanup(tdm_internal_fail(TDM_ERR_CUDA, "cudaEventCreate failed")); } }
     if (cudaMalloc(&h->d_states, sizeof(tdm_bsync_state) * (size_t)n_channels) != cudaSuccess ||
-        cudaMalloc(&h->d_wb, sizeof(uint32_t) * (size_t)n_channels * (size_t)h->wstride) != cudaSuccess ||
+        cudaMalloc(&h->d_wb, 3 * sizeof(uint32_t) * (size_t)n_channels * (size_t)h->wstride) != cudaSuccess ||
         cudaMalloc(&h->d_last_hit, sizeof(int) * (size_t)n_channels) != cudaSuccess) {
         return cleanup(tdm_internal_fail(TDM_ERR_NOMEM, "tdm_bsync_create: cudaMalloc failed"));
     }
@@ -560,13 +696,14 @@ int tdm_bsync_in(tdm_bsync* h, const uint8_t* in, int64_t in_stride, const int32
     // (per-channel counts that live on the device cannot be checked here: the caller guarantees n_units[c] <= in_stride)
     const bool counts_on_device = n_units && mem_kind == TDM_MEM_DEVICE;
     if (umax > 0 && (!in || (!counts_on_device && in_stride < umax))) { return tdm_internal_fail(TDM_ERR_ARG, "tdm_bsync_in: input pointer / stride"); }
-    if (mem_kind == TDM_MEM_DEVICE && bursts && (reinterpret_cast<uintptr_t>(bursts) & 15u)) { return tdm_internal_fail(TDM_ERR_ARG, "tdm_bsync_in: bursts must be 16-byte aligned"); }
+    if (mem_kind == TDM_MEM_DEVICE && bursts && (reinterpret_cast<uintptr_t>(bursts) & 3u)) { return tdm_internal_fail(TDM_ERR_ARG, "tdm_bsync_in: bursts must be 4-byte aligned"); }
     DevGuard guard(h->device);
 
     BsyncParams p{};
     p.in_stride = in_stride; p.units_all = units_all; p.bits_per_unit = in_kind == TDM_BSYNC_IN_DIBITS ? 2 : 1;
     p.max_units = (int)h->max_units;
     p.n_channels = C; p.states = h->d_states; p.wb = h->d_wb; p.wstride = h->wstride; p.last_hit = h->d_last_hit;
+    p.my = h->d_wb + (size_t)C * (size_t)h->wstride; p.mnp = p.my + (size_t)C * (size_t)h->wstride;
     p.call_bits = call_bits; p.max_bursts = max_bursts; p.detect_ts = detect_ts ? 1 : 0;
     if (mem_kind == TDM_MEM_DEVICE) {
         p.in = in; p.n_units = n_units; p.bursts = bursts; p.n_bursts = n_bursts;
@@ -592,11 +729,12 @@ int tdm_bsync_in(tdm_bsync* h, const uint8_t* in, int64_t in_stride, const int32
     bsync_pack_kernel<<<gpack, 256, 0, h->stream>>>(p);
     h->launches++;
     cudaEventRecord(h->ev[1], h->stream);
-    h->ev_detect = p.detect_ts != 0;
-    if (p.detect_ts) {
-        const long long words = (umax * p.bits_per_unit + 31) / 32 + 1;
-        dim3 gdet((unsigned)((words + 255) / 256), (unsigned)C);
-        bsync_detect_kernel<<<gdet, 256, 0, h->stream>>>(p);
+    h->ev_detect = true;
+    {
+        const long long words = (TDM_BSYNC_BITBUF + umax * p.bits_per_unit + 31) / 32;
+        dim3 gm((unsigned)((words + 255) / 256), (unsigned)C);
+        if (p.detect_ts) { bsync_match_kernel<true><<<gm, 256, 0, h->stream>>>(p); }
+        else { bsync_match_kernel<false><<<gm, 256, 0, h->stream>>>(p); }
         h->launches++;
     }
     cudaEventRecord(h->ev[2], h->stream);
@@ -661,10 +799,17 @@ int tdm_find_train_seq(int32_t device, void* cuda_stream, const uint8_t* in, int
 }
 
 // tetra_burst_rx_cb's block split (phy/tetra_burst.c:33-49,343-393); host only.
+int tdm_burst_unpack(const tdm_burst* b, uint8_t* bits510) {
+    if (!b || !bits510) { return tdm_internal_fail(TDM_ERR_ARG, "tdm_burst_unpack: null argument"); }
+    for (int i = 0; i < TDM_BITS_PER_TS; ++i) { bits510[i] = (uint8_t)((b->bits[i >> 5] >> (31 - (i & 31))) & 1u); }
+    return TDM_OK;
+}
+
 int tdm_burst_demux(const tdm_burst* b, tdm_tp_sap_block* out) {
     if (!b || !out) { return tdm_internal_fail(TDM_ERR_ARG, "tdm_burst_demux: null argument"); }
     enum { SB1 = 0, SB2 = 1, NDB = 2, BBK = 3, SCH_F = 5 };       // enum tp_sap_data_type, phy/tetra_burst.h:9-16
-    const uint8_t* u = b->bits;
+    uint8_t u[512];
+    tdm_burst_unpack(b, u);
     std::memset(out, 0, 3 * sizeof(*out));
     auto put = [&](int k, int type, int blk, int off, int n, int at = 0) {
         out[k].type = type; out[k].blk_num = blk; out[k].n_bits = at + n;

@@ -109,7 +109,7 @@ def test_dibit_input_equals_bit_input(pkg, torch_cuda):
             nb2, bu2 = b.feed(torch.from_numpy(drows).cuda(), torch.from_numpy(dn).cuda(), dibits=True, call_bits=333, max_bursts=20, detect_ts=True)
             torch.cuda.synchronize()
             assert torch.equal(nb1, nb2)
-            v1, v2 = pkg.bursts_view(bu1), pkg.bursts_view(bu2)
+            v1, v2 = pkg.bursts_raw(bu1), pkg.bursts_raw(bu2)
             for c in range(C_):
                 k = int(nb1[c])
                 assert v1[c, :k].tobytes() == v2[c, :k].tobytes()

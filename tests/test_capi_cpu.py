@@ -117,10 +117,15 @@ def test_burst_demux_is_host_only_and_matches_the_restatement(pkg):
     rng = np.random.default_rng(4)
     P = B.PortBsync(1)
     for typ, bits in [(B.TRAIN_SYNC, B.sync_burst(rng)), (B.TRAIN_NORM_1, B.norm_burst(rng, False)), (B.TRAIN_NORM_2, B.norm_burst(rng, True))]:
-        rec = np.zeros(1, dtype=pkg.capi.BURST_DTYPE)
+        rec = np.zeros(1, dtype=pkg.capi.BURST_UNPACKED_DTYPE)       # same layout as the checker's record
         rec["train_seq"] = typ
         rec["bits"][0, :510] = bits
-        mine, ref = pkg.burst_demux(rec[0]), P.demux(rec[0])
+        mine, ref = pkg.burst_demux(rec[0]), P.demux(rec[0])         # burst_demux packs it for the ABI
+        packed = np.zeros(1, dtype=pkg.capi.BURST_DTYPE)
+        packed["bits"][0] = np.packbits(rec["bits"][0]).view(">u4").astype(np.uint32)
+        back = np.zeros(510, dtype=np.uint8)
+        assert pkg.capi.lib().tdm_burst_unpack(packed.ctypes.data_as(C.c_void_p), back.ctypes.data_as(C.c_void_p)) == 0
+        assert np.array_equal(back, bits)
         assert len(mine) == len(ref) and len(mine) in (2, 3)
         for f in ["type", "blk_num", "n_bits", "bits"]:
             assert np.array_equal(mine[f], ref[f]), (typ, f)

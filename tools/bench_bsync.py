@@ -151,7 +151,7 @@ def main():
         "config": {"workload": f"{C_} channels x {S} symbols ({'bits' if args.bits else 'dibits'} 1/byte), continuous downlink bursts, BER 1e-3, "
                                f"{args.call_bits}-bit calls, detector {'on' if args.detect else 'off'}", "l2": "inputs larger than L2",
                    "locked_channels_frac": locked, "bursts_per_channel_min": int(nbh.min())},
-        "kernel_ms": {"pack": round(float(kms[0]), 3), "detect": round(float(kms[1]), 3), "sync": round(float(kms[2]), 3)},
+        "kernel_ms": {"pack": round(float(kms[0]), 3), "match": round(float(kms[1]), 3), "sync": round(float(kms[2]), 3)},
         "e2e": e2e, "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "kernel": "bsync_pack_kernel", "achieved": round(ach, 1), "peak": peak, "unit": "GB/s",
                      "frac": round(ach / peak, 4), "traffic": None, "peak_source": src,
