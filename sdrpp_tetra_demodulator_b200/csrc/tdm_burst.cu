@@ -32,8 +32,7 @@
 
 namespace {
 
-constexpr int kTileBits = 16384;                // logical bits per pack CTA: 2-4 16-byte loads in flight per thread
-constexpr int kTileWords = kTileBits / 32;
+constexpr int kTileUnits = 16384;               // input bytes per pack CTA (16384 or 32768 bits): 4 16-byte loads in flight per thread
 constexpr int kPadWords = 8;                    // readable words past the last bit of a row (64-bit window loads)
 
 // training sequences as left-aligned numbers (first bit = most significant), phy/tetra_burst.c:61-72
@@ -92,65 +91,71 @@ __device__ __forceinline__ int units_of(const BsyncParams& p, int c) {
 __device__ __forceinline__ uint32_t pack4_bits(uint32_t x) { return (((x & 0x01010101u) * 0x08040201u) >> 24) & 0xfu; }
 __device__ __forceinline__ uint32_t pack4_dibits(uint32_t x) { return (((x & 0x03030303u) * 0x40100401u) >> 24) & 0xffu; }
 
+// 16 input bytes around the ends of a row or from a row that is not 16-byte aligned: byte loads, zero outside
+// [0, nu).  Deliberately NOT inlined: inlined, ptxas if-converts its 16 guarded loads into ~80 predicated
+// instructions that every thread of the kernel issues (the first version of the pack kernel was issue bound at
+// 0.37 warp instructions per input byte because of that).
+__device__ __noinline__ uint4 load16_edge(const uint8_t* __restrict__ row, long long ua, int nu) {
+    uint32_t w[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        uint32_t acc = 0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const long long u = ua + 4 * q + k;
+            const uint32_t b = (u >= 0 && u < nu) ? (uint32_t)row[u] : 0u;
+            acc |= b << (8 * k);
+        }
+        w[q] = acc;
+    }
+    return make_uint4(w[0], w[1], w[2], w[3]);
+}
+
 __global__ void __launch_bounds__(256) bsync_pack_kernel(const BsyncParams p) {
-    constexpr int kMaxGroups = kTileBits / 16 + 1;                          // 16 units per group; bits: 1025, dibits: 513
-    __shared__ uint16_t s16[kMaxGroups + 7];
+    constexpr int kGroups = kTileUnits / 16 + 1;                            // 16 units per group, one extra for the re-alignment
+    __shared__ uint16_t s16[2 * kGroups + 6];
     const int c = blockIdx.y;
     const int bpu = p.bits_per_unit;
+    const int tile_bits = kTileUnits * bpu, tile_words = tile_bits / 32;
     const int nu = units_of(p, c);
     const long long nbits = (long long)nu * bpu;
     const int cl = p.states ? (int)p.states[c].bits_in_buf : 0;
     const long long total = cl + nbits;
-    const long long tile0 = (long long)blockIdx.x * kTileBits;              // first logical bit of this tile
+    const long long tile0 = (long long)blockIdx.x * tile_bits;              // first logical bit of this tile
     if (blockIdx.x == 0 && threadIdx.x == 0 && p.last_hit) { p.last_hit[c] = 0; }
     if (tile0 >= total + 32 * kPadWords) { return; }
     const uint8_t* __restrict__ row = p.in + (long long)c * p.in_stride;
     const long long ib0 = tile0 - cl;                                       // first input bit of the tile (may be < 0)
     const long long u0 = ib0 >= 0 ? ib0 / bpu : -((-ib0 + bpu - 1) / bpu);  // floor(ib0 / bpu)
     const long long A = u0 & ~15LL;                                         // aligned first unit staged
-    const int groups = kTileBits / (16 * bpu) + 1;
     const bool aligned = ((reinterpret_cast<uintptr_t>(row) & 15u) == 0);
-    constexpr int kPer = (kMaxGroups + 255) / 256;                          // groups per thread: all loads first, then the packing
-    uint32_t w[kPer][4];
+    constexpr int kPer = (kGroups + 255) / 256;                             // groups per thread: all loads first, then the packing
+    uint4 w[kPer];
 #pragma unroll
     for (int r = 0; r < kPer; ++r) {
         const int g = threadIdx.x + 256 * r;
         const long long ua = A + 16LL * g;
-        w[r][0] = w[r][1] = w[r][2] = w[r][3] = 0u;
-        if (g < groups) {
-            if (ua >= 0 && ua + 16 <= nu && aligned) {
-                const uint4 v = __ldg(reinterpret_cast<const uint4*>(row + ua));
-                w[r][0] = v.x; w[r][1] = v.y; w[r][2] = v.z; w[r][3] = v.w;
-            } else if (ua + 16 > 0 && ua < nu) {
-#pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    uint32_t acc = 0;
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        const long long u = ua + 4 * q + k;
-                        const uint32_t b = (u >= 0 && u < nu) ? (uint32_t)row[u] : 0u;
-                        acc |= b << (8 * k);
-                    }
-                    w[r][q] = acc;
-                }
-            }
+        w[r] = make_uint4(0u, 0u, 0u, 0u);
+        if (g < kGroups) {
+            if (ua >= 0 && ua + 16 <= nu && aligned) { w[r] = __ldg(reinterpret_cast<const uint4*>(row + ua)); }
+            else if (ua + 16 > 0 && ua < nu) { w[r] = load16_edge(row, ua, nu); }
         }
     }
 #pragma unroll
     for (int r = 0; r < kPer; ++r) {
         const int g = threadIdx.x + 256 * r;
-        if (g < groups) {
+        if (g < kGroups) {
             if (bpu == 1) {
-                s16[g] = (uint16_t)((pack4_bits(w[r][0]) << 12) | (pack4_bits(w[r][1]) << 8) | (pack4_bits(w[r][2]) << 4) | pack4_bits(w[r][3]));
+                s16[g] = (uint16_t)((pack4_bits(w[r].x) << 12) | (pack4_bits(w[r].y) << 8) | (pack4_bits(w[r].z) << 4) | pack4_bits(w[r].w));
             } else {
-                s16[2 * g] = (uint16_t)((pack4_dibits(w[r][0]) << 8) | pack4_dibits(w[r][1]));
-                s16[2 * g + 1] = (uint16_t)((pack4_dibits(w[r][2]) << 8) | pack4_dibits(w[r][3]));
+                reinterpret_cast<uint32_t*>(s16)[g] = ((pack4_dibits(w[r].z) << 24) | (pack4_dibits(w[r].w) << 16)) |
+                                                      ((pack4_dibits(w[r].x) << 8) | pack4_dibits(w[r].y));     // s16[2g] = first 16 bits (little endian halves)
             }
         }
     }
     __syncthreads();
-    for (int t = threadIdx.x; t < kTileWords; t += 256) {
-        const long long wi = (long long)blockIdx.x * kTileWords + t;
+    for (int t = threadIdx.x; t < tile_words; t += 256) {
+        const long long wi = (long long)blockIdx.x * tile_words + t;
         if (wi * 32 < total + 32 * kPadWords && wi < p.wstride) {
             const int o = (int)(ib0 - A * bpu) + 32 * t;                    // bit offset into the staged bits
             const int idx = o >> 4, sh = o & 15;
@@ -176,7 +181,7 @@ __device__ __forceinline__ unsigned long long load64(const uint32_t* __restrict_
 // the ~8 search steps of a call wait for DRAM (5200 cycles per call measured).  The window is a shared-memory
 // copy of kWinWords consecutive row words, refilled with coalesced loads only when a search leaves it
 // (about every 11th call while locked).  With cache == nullptr it reads the row directly (stateless find).
-constexpr int kWinWords = 192;                  // 6144 bits >= the 4096-bit buffer + look-ahead
+constexpr int kWinWords = 512;                  // 16384 bits: the 4096-bit buffer + look-ahead, or one batch of 32 speculative calls
 struct RowWindow {
     const uint32_t* __restrict__ rowp;          // packed bits
     const uint32_t* __restrict__ myp;           // match bitmaps (null for the stateless find)
@@ -400,6 +405,72 @@ __device__ __forceinline__ int warp_find_bitmap(RowWindow& win, long long ps, ui
     return -1;
 }
 
+// warp_find_bitmap for ONE lane working on its own buffer (mask {NORM_1, NORM_2, SYNC}); the window must already
+// cover [ps, ps + len + 64).  Used by the speculative slot-parallel path of the sync kernel.
+__device__ __forceinline__ int lane_find_bitmap(const RowWindow& win, long long ps, uint32_t len, uint32_t& offset) {
+    const uint32_t mask = (1u << TDM_TRAIN_NORM_1) | (1u << TDM_TRAIN_NORM_2) | (1u << TDM_TRAIN_SYNC);
+    if (len < 22) { return -1; }
+    {
+        const long long w0 = ps >> 5;
+        const int sh = (int)(ps & 31);
+        uint32_t head = __funnelshift_l(win.mword(w0 + 1, true), win.mword(w0, true), sh) >> 11;    // positions ps .. ps+20, ps in bit 20
+        if (head) {
+            const unsigned long long W0 = win.get64(ps);
+            while (head) {
+                const int i = 20 - (31 - __clz(head));
+                head &= ~(1u << (20 - i));
+                if (len - (uint32_t)i < 22) { break; }
+                const uint32_t part1 = (uint32_t)(W0 >> 44) & ((1u << (21 - i)) - 1u);
+                const uint32_t part2 = (uint32_t)(W0 >> (42 - i)) & ((1u << (i + 1)) - 1u);
+                const uint32_t f = (part1 << (i + 1)) | part2;
+                if (f == kPreY || f == (uint32_t)kSeqN || f == (uint32_t)kSeqP || f == (uint32_t)kSeqQ || f == kPreX) {
+                    const int t = match_train_seq(win.get64(ps + i), len - (uint32_t)i, mask);
+                    if (t >= 0) { offset = (uint32_t)i; return t; }
+                }
+            }
+        }
+    }
+    const long long lo = ps + 21, hi = ps + (long long)len - 21;
+    for (long long wi = lo >> 5; wi * 32 < hi; ++wi) {
+        const long long L0 = wi * 32;
+        uint32_t m = win.mword(wi, true);
+        if (L0 < lo) { m &= 0xffffffffu >> (int)(lo - L0); }
+        if (L0 + 32 > hi) { m &= ~(0xffffffffu >> (int)(hi - L0)); }
+        while (m) {
+            const int q = __clz(m);
+            const long long pos = L0 + q;
+            const int t = match_train_seq(win.get64(pos), (uint32_t)(ps + len - pos), mask);
+            if (t >= 0) { offset = (uint32_t)(pos - ps); return t; }
+            m &= ~(0x80000000u >> q);
+        }
+    }
+    return -1;
+}
+
+// m >= 1 calls of tetra_tdma_time_add_tn(&time, 1) in closed form (tetra_tdma.c:27-74: each counter wraps from its
+// maximum back to 1 and carries one into the next; a counter that still holds its initial 0 simply counts up).
+__device__ __forceinline__ void advance_time(uint32_t& tn, uint32_t& fn, uint32_t& mn, uint32_t m) {
+    if (m == 0 || tn > 4 || fn > 18 || mn > 60) {                           // states the reference itself never produces: step by step
+        for (uint32_t i = 0; i < m; ++i) {
+            tn += 1;
+            if (tn > 4) { const uint32_t d = tn / 4; tn %= 4; fn += d; }
+            if (fn > 18) { const uint32_t d = fn / 18; fn %= 18; mn += d; }
+            if (mn > 60) { mn %= 60; }
+        }
+        return;
+    }
+    const int t = (int)tn - 1 + (int)m;                                    // >= 0
+    const uint32_t w1 = (uint32_t)(t / 4);
+    tn = (uint32_t)(t % 4) + 1u;
+    if (w1 == 0) { return; }
+    const int f = (int)fn - 1 + (int)w1;
+    const uint32_t w2 = (uint32_t)(f / 18);
+    fn = (uint32_t)(f % 18) + 1u;
+    if (w2 == 0) { return; }
+    const int q = (int)mn - 1 + (int)w2;
+    mn = (uint32_t)(q % 60) + 1u;
+}
+
 // ---------------------------------------------------------------------------------------------------
 // sync: one warp per channel replays tetra_burst_sync_in call by call.
 // ---------------------------------------------------------------------------------------------------
@@ -441,64 +512,126 @@ __global__ void __launch_bounds__(128) bsync_fsm_kernel(const BsyncParams p) {
 
     uint32_t nb = 0, call = 0;
     const uint32_t call_bits = (uint32_t)p.call_bits;
-    for (uint32_t off = 0; off < n; off += call_bits, ++call) {
-        const uint32_t len = n - off < call_bits ? n - off : call_bits;
-        const uint32_t space = TDM_BSYNC_BITBUF - bib;
-        if (space < len) { const uint32_t delta = len - space; bib -= delta; start += delta; }   // make_bitbuf_space
-        bib += len;
-        const long long ps = (long long)(start - base);
-        uint32_t offs = 0;
-        if (state == TDM_RX_S_UNLOCKED) {
-            if (bib < 2 * TDM_BITS_PER_TS) { continue; }
-            if ((int32_t)(cursor - start) < 0) { cursor = start; }
-            const int rc = warp_find_bitmap(win, ps, bib, false, (long long)(cursor - base), offs);
-            if (rc < 0) {
-                cursor = start + bib - 37;           // positions up to end - 38 had all 38 bits and did not hold y
-                continue;
+    uint32_t off = 0;
+    while (off < n) {
+        if (state == TDM_RX_S_LOCKED && bib + call_bits <= TDM_BSYNC_BITBUF) {
+            // ---- LOCKED: slot-parallel replay.  While the receiver stays LOCKED, what call k sees is known in
+            // advance: the buffer gains call_bits per call and loses one slot per call whenever it holds 510 bits, so
+            // with a_k = bib + (bits of calls 0..k), S_k = min(k + 1, floor(a_k / 510)) slots are gone after call k
+            // (a queue served at most once per step whose arrivals complete at most one slot per step; the buffer
+            // cannot overflow because it never grows while it holds a slot).  Lane k replays call k on its own; the
+            // first lane that would leave LOCKED ends the batch, later lanes are discarded and replayed.
+            const uint32_t remaining = n - off;
+            const uint32_t ncalls = (remaining + call_bits - 1) / call_bits;
+            // the buffers of all calls of a batch must fit into the window together
+            const uint32_t fit = ((uint32_t)(32 * kWinWords - 200) - bib) / call_bits;
+            const uint32_t B = min(min(32u, ncalls), fit);                  // >= 1: bib + call_bits <= 4096
+            const long long ps0 = (long long)(start - base);
+            const uint32_t span = B * call_bits < remaining ? B * call_bits : remaining;
+            win.ensure(ps0, bib + span);
+            const bool active = (uint32_t)lane < B;
+            const uint32_t arr_prev = min((uint32_t)lane * call_bits, remaining);
+            const uint32_t arr = min(((uint32_t)lane + 1u) * call_bits, remaining);
+            const uint32_t cons_before = min((uint32_t)lane, (bib + arr_prev) / TDM_BITS_PER_TS);
+            const uint32_t cons_after = min((uint32_t)lane + 1u, (bib + arr) / TDM_BITS_PER_TS);
+            const bool proc = active && cons_after > cons_before;          // this call finds a whole slot in the buffer
+            const uint32_t bibf = bib + arr - TDM_BITS_PER_TS * cons_before;
+            const long long psk = ps0 + (long long)TDM_BITS_PER_TS * cons_before;
+            uint32_t offs = 0;
+            int rc = -1;
+            if (proc) { rc = lane_find_bitmap(win, psk, bibf, offs); }
+            const bool is_sync = rc == TDM_TRAIN_SYNC, is_norm = rc == TDM_TRAIN_NORM_1 || rc == TDM_TRAIN_NORM_2;
+            const bool deliver = proc && ((is_sync && offs == 214) || (is_norm && offs == 244));
+            const bool unlock = proc && !deliver && !is_norm;              // SYNC at the wrong place, or nothing found
+            const unsigned ub = __ballot_sync(0xffffffffu, unlock);
+            const uint32_t last = ub ? (uint32_t)(__ffs(ub) - 1) : B - 1u;  // last call of the batch that really happens
+            const bool committed = active && (uint32_t)lane <= last;
+            const unsigned db = __ballot_sync(0xffffffffu, committed && deliver);
+            if (committed && deliver) {
+                const uint32_t idx = nb + (uint32_t)__popc(db & ((1u << lane) - 1u));
+                if (idx < (uint32_t)p.max_bursts && p.bursts) {
+                    tdm_burst* b = p.bursts + ((long long)c * p.max_bursts + idx);
+                    uint32_t t1 = tn, f1 = fn, m1 = mn;
+                    advance_time(t1, f1, m1, cons_after);
+                    b->bitnum = start + TDM_BITS_PER_TS * cons_before; b->train_seq = rc; b->tn = t1; b->fn = f1; b->mn = m1;
+                    b->call_index = call + (uint32_t)lane; b->reserved[0] = 0; b->reserved[1] = 0;
+#pragma unroll
+                    for (int k = 0; k < 16; ++k) {
+                        uint32_t v = (uint32_t)(win.get64(psk + 32 * k) >> 32);
+                        if (k == 15) { v &= 0xfffffffcu; }
+                        b->bits[k] = v;
+                    }
+                }
             }
-            state = TDM_RX_S_KNOW_FSTART;
-            nfs = start + offs + 296;
+            const uint32_t arr_c = min((last + 1u) * call_bits, remaining);
+            const uint32_t cons_c = min(last + 1u, (bib + arr_c) / TDM_BITS_PER_TS);
+            advance_time(tn, fn, mn, cons_c);
+            bib = bib + arr_c - TDM_BITS_PER_TS * cons_c;
+            start += TDM_BITS_PER_TS * cons_c; nfs += TDM_BITS_PER_TS * cons_c;
+            nb += (uint32_t)__popc(db);
+            off += arr_c; call += last + 1u;
+            if (ub) { state = TDM_RX_S_UNLOCKED; cursor = start; }
             continue;
         }
-        if (state == TDM_RX_S_KNOW_FSTART) {
-            if (start + bib < nfs) { continue; }
-            uint32_t shift = nfs - start;
-            if ((int32_t)shift < 0) { shift = 0; }   // undefined in the reference; see tdm_burst_b200.h
-            bib -= shift; start += shift;
-            nfs += TDM_BITS_PER_TS;
-            state = TDM_RX_S_LOCKED;                 // falls through into the LOCKED case, like the reference
-        }
-        if (bib < TDM_BITS_PER_TS) { continue; }
-        tn += 1;                                     // tetra_tdma_time_add_tn(&time, 1)
-        if (tn > 4) { const uint32_t d = tn / 4; tn %= 4; fn += d; }
-        if (fn > 18) { const uint32_t d = fn / 18; fn %= 18; mn += d; }
-        if (mn > 60) { mn %= 60; }
-        const long long ps2 = (long long)(start - base);
-        const int rc = warp_find_bitmap(win, ps2, bib, true, ps2, offs);
-        bool deliver = false;
-        if (rc == TDM_TRAIN_SYNC) {
-            if (offs == 214) { deliver = true; } else { state = TDM_RX_S_UNLOCKED; cursor = start + TDM_BITS_PER_TS; }
-        } else if (rc == TDM_TRAIN_NORM_1 || rc == TDM_TRAIN_NORM_2) {
-            deliver = (offs == 244);
-        } else {
-            state = TDM_RX_S_UNLOCKED; cursor = start + TDM_BITS_PER_TS;
-        }
-        if (deliver) {
-            if (nb < (uint32_t)p.max_bursts && p.bursts) {
-                tdm_burst* b = p.bursts + ((long long)c * p.max_bursts + nb);
-                if (lane == 16) {
-                    b->bitnum = start; b->train_seq = rc; b->tn = tn; b->fn = fn; b->mn = mn; b->call_index = call;
-                    b->reserved[0] = 0; b->reserved[1] = 0;
+        // ---- one call, the whole warp on it (acquisition, and LOCKED with more than a slot buffered)
+        const uint32_t len = n - off < call_bits ? n - off : call_bits;
+        off += len;
+        const uint32_t this_call = call++;
+        do {
+            const uint32_t space = TDM_BSYNC_BITBUF - bib;
+            if (space < len) { const uint32_t delta = len - space; bib -= delta; start += delta; }   // make_bitbuf_space
+            bib += len;
+            const long long ps = (long long)(start - base);
+            uint32_t offs = 0;
+            if (state == TDM_RX_S_UNLOCKED) {
+                if (bib < 2 * TDM_BITS_PER_TS) { break; }
+                if ((int32_t)(cursor - start) < 0) { cursor = start; }
+                const int rc = warp_find_bitmap(win, ps, bib, false, (long long)(cursor - base), offs);
+                if (rc < 0) {
+                    cursor = start + bib - 37;       // positions up to end - 38 had all 38 bits and did not hold y
+                    break;
                 }
-                if (lane < 16) {                                                    // the burst is already packed: 16 words
-                    uint32_t v = (uint32_t)(win.get64(ps2 + 32 * lane) >> 32);
-                    if (lane == 15) { v &= 0xfffffffcu; }                           // bits 510, 511 do not exist
-                    b->bits[lane] = v;
-                }
+                state = TDM_RX_S_KNOW_FSTART;
+                nfs = start + offs + 296;
+                break;
             }
-            ++nb;
-        }
-        bib -= TDM_BITS_PER_TS; start += TDM_BITS_PER_TS; nfs += TDM_BITS_PER_TS;
+            if (state == TDM_RX_S_KNOW_FSTART) {
+                if (start + bib < nfs) { break; }
+                uint32_t shift = nfs - start;
+                if ((int32_t)shift < 0) { shift = 0; }   // undefined in the reference; see tdm_burst_b200.h
+                bib -= shift; start += shift;
+                nfs += TDM_BITS_PER_TS;
+                state = TDM_RX_S_LOCKED;             // falls through into the LOCKED case, like the reference
+            }
+            if (bib < TDM_BITS_PER_TS) { break; }
+            advance_time(tn, fn, mn, 1);             // tetra_tdma_time_add_tn(&time, 1)
+            const long long ps2 = (long long)(start - base);
+            const int rc = warp_find_bitmap(win, ps2, bib, true, ps2, offs);
+            bool deliver = false;
+            if (rc == TDM_TRAIN_SYNC) {
+                if (offs == 214) { deliver = true; } else { state = TDM_RX_S_UNLOCKED; cursor = start + TDM_BITS_PER_TS; }
+            } else if (rc == TDM_TRAIN_NORM_1 || rc == TDM_TRAIN_NORM_2) {
+                deliver = (offs == 244);
+            } else {
+                state = TDM_RX_S_UNLOCKED; cursor = start + TDM_BITS_PER_TS;
+            }
+            if (deliver) {
+                if (nb < (uint32_t)p.max_bursts && p.bursts) {
+                    tdm_burst* b = p.bursts + ((long long)c * p.max_bursts + nb);
+                    if (lane == 16) {
+                        b->bitnum = start; b->train_seq = rc; b->tn = tn; b->fn = fn; b->mn = mn; b->call_index = this_call;
+                        b->reserved[0] = 0; b->reserved[1] = 0;
+                    }
+                    if (lane < 16) {                                                // the burst is already packed: 16 words
+                        uint32_t v = (uint32_t)(win.get64(ps2 + 32 * lane) >> 32);
+                        if (lane == 15) { v &= 0xfffffffcu; }                       // bits 510, 511 do not exist
+                        b->bits[lane] = v;
+                    }
+                }
+                ++nb;
+            }
+            bib -= TDM_BITS_PER_TS; start += TDM_BITS_PER_TS; nfs += TDM_BITS_PER_TS;
+        } while (0);
     }
 
     // carry the buffered bits [start, start + bib) to the front of the state's packed buffer
@@ -724,7 +857,8 @@ int tdm_bsync_in(tdm_bsync* h, const uint8_t* in, int64_t in_stride, const int32
         p.bursts = h->d_bursts; p.n_bursts = h->d_nbursts;
     }
     const long long row_bits = TDM_BSYNC_BITBUF + umax * p.bits_per_unit + 32 * kPadWords;
-    dim3 gpack((unsigned)((row_bits + kTileBits - 1) / kTileBits), (unsigned)C);
+    const long long tile_bits = (long long)kTileUnits * p.bits_per_unit;
+    dim3 gpack((unsigned)((row_bits + tile_bits - 1) / tile_bits), (unsigned)C);
     cudaEventRecord(h->ev[0], h->stream);
     bsync_pack_kernel<<<gpack, 256, 0, h->stream>>>(p);
     h->launches++;
@@ -786,7 +920,7 @@ int tdm_find_train_seq(int32_t device, void* cuda_stream, const uint8_t* in, int
         p.in = d_in; p.in_stride = end_of_in; p.find_type = d_type; p.find_offset = d_off;
     }
     const long long row_bits = (long long)end_of_in + 32 * kPadWords;
-    dim3 gpack((unsigned)((row_bits + kTileBits - 1) / kTileBits), (unsigned)n_channels);
+    dim3 gpack((unsigned)((row_bits + kTileUnits - 1) / kTileUnits), (unsigned)n_channels);
     bsync_pack_kernel<<<gpack, 256, 0, stream>>>(p);
     bsync_find_kernel<<<(n_channels + 3) / 4, 128, 0, stream>>>(p);
     if (cudaGetLastError() != cudaSuccess) { return done(tdm_internal_fail(TDM_ERR_CUDA, "tdm_find_train_seq: launch failed")); }

@@ -9,12 +9,13 @@ import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 BIN = os.path.join(ROOT, "sdrpp_tetra_demodulator_b200", "host", "test_host_block")
+BIN_BSYNC = os.path.join(ROOT, "sdrpp_tetra_demodulator_b200", "host", "test_host_bsync")
 
 
 def test_host_block_builds_against_sdrpp_surface():
     """compile check (no GPU): the block sources build against the SDR++-shaped headers and link the C ABI"""
     subprocess.run(["make", "-C", os.path.dirname(BIN)], check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
-    assert os.path.exists(BIN)
+    assert os.path.exists(BIN) and os.path.exists(BIN_BSYNC)
 
 
 @pytest.mark.gpu
@@ -38,3 +39,34 @@ def test_threaded_block_chain_matches_oracle(O, tmp_path, buffer_samples):
     assert len(got) == 2 * n, (len(got), 2 * n, r.stdout)
     assert np.array_equal(got, bits[0, :2 * n])
     assert "sync 1" in r.stdout
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("buffer_bits", [432, 510, 2000])
+def test_threaded_burst_sync_block_matches_checker(pkg, tmp_path, buffer_bits):
+    """dsp::b200::BurstSync on its own worker thread (the front of dsp::osmotetradec, src/dsp/osmotetra_dec.h:183):
+    one input buffer = one tetra_burst_sync_in call (510-bit calls when a buffer holds more than a slot)"""
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from oracle import oracle_bsync as B
+    B.build()
+    if not os.path.exists(BIN_BSYNC):
+        subprocess.run(["make", "-C", os.path.dirname(BIN_BSYNC)], check=True)
+    bits = B.downlink_stream(77, 50, ber=1e-3, glitch_at=(20,))
+    port = B.PortBsync(1)
+    want = []
+    for p0 in range(0, len(bits), buffer_bits):
+        part = bits[p0:p0 + buffer_bits]
+        nb, bu = port.feed(part[None, :], len(part), min(buffer_bits, 510), 8, detect_ts=True)
+        want.extend(bu[0, :nb[0]])
+    fin, fout = tmp_path / "in.bits", tmp_path / "out.bursts"
+    bits.tofile(fin)
+    r = subprocess.run([BIN_BSYNC, str(fin), str(fout), str(buffer_bits)], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stderr
+    got = pkg.bursts_view(np.fromfile(fout, dtype=pkg.capi.BURST_DTYPE).reshape(1, -1))[0]
+    assert len(got) == len(want) and len(want) > 30, (len(got), len(want), r.stdout)
+    for g, w in zip(got, want):
+        for f in ("bitnum", "train_seq", "tn", "fn", "mn", "bits"):
+            assert np.array_equal(g[f], w[f]), f
+    assert f"rx_state {int(port.states[0]['state'])}" in r.stdout and f"ts_found {int(port.states[0]['ts_found'])}" in r.stdout
