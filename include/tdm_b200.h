@@ -175,6 +175,30 @@ int tdm_process(tdm_handle* h, const float* iq, int64_t in_stride, int32_t count
                 float* syms, uint8_t* dibits, uint8_t* bits, int64_t out_stride,
                 int32_t* out_counts, uint32_t out_flags, int32_t mem_kind);
 
+/* ONE long capture of ONE channel, demodulated as up to n_channels overlapping time segments in parallel (SURVEY.md
+ * section 8f rank 4; BASELINE.json configs[1] "1 channel, 1e9 complex samples").  The chain is a recurrence in
+ * time and the reference can only walk it sample by sample (PI4DQPSK::process, src/dsp/pi4dqpsk.cpp:132-140);
+ * here segment c covers samples [c L, (c+1) L + warmup), the first `warmup` samples of every segment but the
+ * first only let its loops converge, and the dibit streams are joined where 128 consecutive dibits agree
+ * (a segment that has not converged in time is demodulated again as the sequential continuation of its
+ * predecessor).  Segment 0 starts from the state the previous tdm_process_long left, so consecutive calls
+ * continue one stream.
+ *
+ * CONTRACT: decoded dibits only.  They equal the sequential chain's (tdm_process on one channel, hence the
+ * reference's) from the point where the sequential chain has locked; before that, and in the float loop states,
+ * the two may differ.  iq: [n_samples] interleaved float pairs; dibits: [dibits_cap] bytes, info->n_dibits
+ * written; n_samples / 2 + 64 is always enough.  Uses the handle's per-channel states as scratch: do not mix with
+ * tdm_process on the same handle. */
+typedef struct tdm_long_info {
+    int64_t n_dibits;          /* dibits written                                                  */
+    int32_t n_segments;        /* segments actually used (fewer for short captures)              */
+    int32_t n_rerun;           /* segments that had to be redone sequentially (join not found)    */
+    int32_t segment_samples;   /* L                                                               */
+    int32_t warmup;            /* W actually used (0 when a single segment was enough)            */
+} tdm_long_info;
+int tdm_process_long(tdm_handle* h, const float* iq, int64_t n_samples, int32_t warmup, uint8_t* dibits, int64_t dibits_cap,
+                     tdm_long_info* info, int32_t mem_kind);
+
 /* PI4DQPSK::reset (src/dsp/pi4dqpsk.cpp:120-130): loop scalars back to their
  * initial values, RRC history cleared, FLL/timing histories KEPT (fll.cpp:120-127,
  * complex_fd.cpp:78-87).  tdm_reset_all additionally clears every history and

@@ -40,6 +40,7 @@ EXPORTED_SYMBOLS = [
     "tdm_max_symbols", "tdm_process", "tdm_reset", "tdm_reset_all", "tdm_get_state", "tdm_set_state",
     "tdm_get_metrics", "tdm_set_config", "tdm_get_design", "tdm_set_kernel_variant", "tdm_last_kernel_ms",
     "tdm_launch_count", "tdm_pack_dibits", "tdm_synth_capture", "tdm_last_error", "tdm_abi_version",
+    "tdm_process_long",
 ]
 # ... and include/tdm_burst_b200.h
 EXPORTED_BURST_SYMBOLS = [
@@ -83,6 +84,11 @@ class TdmDesign(C.Structure):
 class TdmSynthParams(C.Structure):
     _fields_ = [("snr_db", C.c_double), ("max_freq_off_hz", C.c_double), ("min_amp", C.c_double),
                 ("max_amp", C.c_double), ("seed_data", C.c_uint64), ("seed_noise", C.c_uint64)]
+
+
+class TdmLongInfo(C.Structure):
+    _fields_ = [("n_dibits", C.c_int64), ("n_segments", C.c_int32), ("n_rerun", C.c_int32),
+                ("segment_samples", C.c_int32), ("warmup", C.c_int32)]
 
 
 class TdmMetrics(C.Structure):
@@ -157,6 +163,7 @@ def lib() -> C.CDLL:
         "tdm_synth_capture": (C.c_int, [i32, vp, C.POINTER(TdmSynthParams), i32, i64, i64, i32, vp, vp, i64]),
         "tdm_last_error": (C.c_char_p, []),
         "tdm_abi_version": (C.c_int, []),
+        "tdm_process_long": (C.c_int, [vp, vp, i64, i32, vp, i64, C.POINTER(TdmLongInfo), i32]),
         "tdm_bsync_create": (C.c_int, [i32, i64, i32, C.POINTER(vp)]),
         "tdm_bsync_destroy": (C.c_int, [vp]),
         "tdm_bsync_set_stream": (C.c_int, [vp, vp]),

@@ -77,6 +77,14 @@ struct tdm_handle {
     uint8_t* d_dibits = nullptr;
     uint8_t* d_bits = nullptr;
     int* d_counts = nullptr;
+    // tdm_process_long: the logical channel's carried state [0] + a freshly initialised state [1]; per-segment scratch
+    tdm_channel_state* d_long_state = nullptr;
+    tdm_channel_state* d_states2 = nullptr;
+    uint8_t* d_seg_dibits = nullptr;
+    uint8_t* d_seg_dibits2 = nullptr;
+    long long seg_stride = 0, seg_stride2 = 0;
+    int* d_seg_ints = nullptr;                   // counts[S], counts2[S], join[S], fixed[S], adopt[S], n_open, tail count
+    long long* d_offs = nullptr;                 // [S + 1]
 };
 
 namespace {
@@ -189,6 +197,8 @@ int tdm_destroy(tdm_handle* h) {
     if (h->own_stream) { cudaStreamSynchronize(h->own_stream); }
     cudaFree(h->d_bank); cudaFree(h->d_states); cudaFree(h->d_iq); cudaFree(h->d_syms);
     cudaFree(h->d_dibits); cudaFree(h->d_bits); cudaFree(h->d_counts);
+    cudaFree(h->d_long_state); cudaFree(h->d_states2); cudaFree(h->d_seg_dibits); cudaFree(h->d_seg_dibits2);
+    cudaFree(h->d_seg_ints); cudaFree(h->d_offs);
     if (h->ev_start) { cudaEventDestroy(h->ev_start); }
     if (h->ev_stop) { cudaEventDestroy(h->ev_stop); }
     for (auto& e : h->ev_slice) { if (e) { cudaEventDestroy(e); } }
@@ -310,6 +320,151 @@ int tdm_process(tdm_handle* h, const float* iq, int64_t in_stride, int32_t count
     return TDM_OK;
 }
 
+// SURVEY.md 8f rank 4.  See tdm_stitch.cu for the scheme and include/tdm_b200.h for the contract.
+int tdm_process_long(tdm_handle* h, const float* iq, int64_t n_samples, int32_t warmup, uint8_t* dibits, int64_t dibits_cap,
+                     tdm_long_info* info, int32_t mem_kind) {
+    if (!h || !info) { return fail(TDM_ERR_ARG, "tdm_process_long: null handle / info"); }
+    std::memset(info, 0, sizeof(*info));
+    if (n_samples < 0 || (n_samples > 0 && (!iq || !dibits)) || dibits_cap < 0) { return fail(TDM_ERR_ARG, "tdm_process_long: bad buffers"); }
+    if (warmup < 1024 || warmup > (1 << 24)) { return fail(TDM_ERR_ARG, "tdm_process_long: warmup must be 1024..2^24 samples"); }
+    if (mem_kind != TDM_MEM_HOST && mem_kind != TDM_MEM_DEVICE) { return fail(TDM_ERR_ARG, "tdm_process_long: mem_kind"); }
+    if (n_samples == 0) { return TDM_OK; }
+    DeviceGuard guard(h->device);
+    cudaStream_t st = h->stream;
+    const int K = 128;                                          // dibits that must agree at a join (2^-256 for a chance match)
+    // segments: S rows of L + W samples, row c starts at sample c L; a segment must dwarf its warm-up to be worth it
+    int S = h->n_channels;
+    const long long min_seg = 4LL * warmup;
+    if ((n_samples - warmup) / S < min_seg) { S = (int)((n_samples - warmup) / min_seg); }
+    if (S < 1) { S = 1; }
+    long long L = (S > 1) ? (((n_samples - warmup) / S) & ~7LL) : n_samples;
+    const long long W = (S > 1) ? warmup : 0;
+    if (L + W > 0x7fffffffLL) { return fail(TDM_ERR_ARG, "tdm_process_long: segments of %lld samples exceed the 32-bit count of a launch; use more segments", L + W); }
+    const long long covered = (S > 1) ? S * L + W : n_samples;
+    const long long tail = n_samples - covered;                 // < 8 S + S samples, demodulated sequentially at the end
+    const long long need = max_symbols_for(h->design, L + W);
+
+    // scratch
+    if (!h->d_long_state) {
+        TDM_CUDA(cudaMalloc(&h->d_long_state, 2 * sizeof(tdm_channel_state)));
+        tdm_channel_state two[2];
+        init_state(h->design, two[0]);
+        two[1] = two[0];
+        TDM_CUDA(cudaMemcpyAsync(h->d_long_state, two, sizeof(two), cudaMemcpyHostToDevice, st));
+    }
+    const size_t C = (size_t)h->n_channels;
+    if (!h->d_states2) { TDM_CUDA(cudaMalloc(&h->d_states2, sizeof(tdm_channel_state) * C)); }
+    if (!h->d_seg_ints) { TDM_CUDA(cudaMalloc(&h->d_seg_ints, sizeof(int) * (5 * C + 2))); }
+    if (!h->d_offs) { TDM_CUDA(cudaMalloc(&h->d_offs, sizeof(long long) * (C + 1))); }
+    if (h->seg_stride < need) {
+        cudaFree(h->d_seg_dibits); h->d_seg_dibits = nullptr; h->seg_stride = 0;
+        TDM_CUDA(cudaMalloc(&h->d_seg_dibits, C * (size_t)need));
+        h->seg_stride = need;
+    }
+    int* d_counts = h->d_seg_ints;
+    int* d_counts2 = d_counts + C;
+    int* d_join = d_counts2 + C;
+    int* d_fixed = d_join + C;
+    int* d_adopt = d_fixed + C;
+    int* d_nopen = d_adopt + C;
+    int* d_tailcount = d_nopen + 1;
+
+    const float2* d_iq = reinterpret_cast<const float2*>(iq);
+    float2* d_tmp_iq = nullptr;
+    uint8_t* d_out = dibits;
+    uint8_t* d_tmp_out = nullptr;
+    auto done = [&](int code) { cudaFree(d_tmp_iq); cudaFree(d_tmp_out); return code; };
+    if (mem_kind == TDM_MEM_HOST) {
+        if (cudaMalloc(&d_tmp_iq, sizeof(float2) * (size_t)n_samples) != cudaSuccess || cudaMalloc(&d_tmp_out, (size_t)(dibits_cap > 0 ? dibits_cap : 1)) != cudaSuccess) {
+            return done(fail(TDM_ERR_NOMEM, "tdm_process_long: cannot stage %lld samples on the device", (long long)n_samples));
+        }
+        if (cudaMemcpyAsync(d_tmp_iq, iq, sizeof(float2) * (size_t)n_samples, cudaMemcpyHostToDevice, st) != cudaSuccess) {
+            return done(fail(TDM_ERR_CUDA, "tdm_process_long: H2D copy failed"));
+        }
+        d_iq = d_tmp_iq;
+        d_out = d_tmp_out;
+    }
+
+    tdm::DemodParams p;
+    fill_params(h, p);
+    p.n_channels = S;
+    p.syms = nullptr; p.bits = nullptr; p.accumulate = 0;
+    // ---- pass 1: all segments at once, segment 0 from the carried state, the others from reset state
+    tdm::launch_long_init_states(h->d_states, h->d_long_state, h->d_long_state + 1, S, st);
+    p.iq = d_iq; p.in_stride = L; p.count = (int)(L + W);
+    p.dibits = h->d_seg_dibits; p.out_stride = h->seg_stride; p.out_counts = d_counts;
+    int n = tdm::launch_demod(p, h->variant, st);
+    if (n < 0) { return done(fail(TDM_ERR_CUDA, "demod kernel launch failed: %s", cudaGetErrorString(cudaGetLastError()))); }
+    h->launches += n;
+    // ---- joins; segments that find none are redone as the continuation of their predecessor, one per failed run and pass
+    const int mid = (int)(W / 2);
+    int n_rerun = 0;
+    if (S > 1) {
+        if (cudaMemsetAsync(d_fixed, 0, sizeof(int) * (size_t)S, st) != cudaSuccess ||
+            cudaMemcpyAsync(h->d_states2, h->d_states, sizeof(tdm_channel_state) * (size_t)S, cudaMemcpyDeviceToDevice, st) != cudaSuccess) {
+            return done(fail(TDM_ERR_CUDA, "tdm_process_long: %s", cudaGetErrorString(cudaGetLastError())));
+        }
+        tdm_channel_state* d_final = h->d_states2;                     // final loop state of the run whose stream each segment uses
+        for (int pass = 0;; ++pass) {
+            tdm::launch_stitch_find(h->d_seg_dibits, h->seg_stride, d_counts, S, K, mid - 2048, mid + 256, d_join, d_fixed, st);
+            tdm::launch_stitch_plan(d_join, d_fixed, S, d_adopt, d_nopen, st);
+            int n_open = 0;
+            if (cudaMemcpyAsync(&n_open, d_nopen, sizeof(int), cudaMemcpyDeviceToHost, st) != cudaSuccess || cudaStreamSynchronize(st) != cudaSuccess) {
+                return done(fail(TDM_ERR_CUDA, "tdm_process_long: %s", cudaGetErrorString(cudaGetLastError())));
+            }
+            if (n_open == 0) { break; }
+            if (pass >= 64) { return done(fail(TDM_ERR_UNSUPPORTED, "tdm_process_long: %d segments still do not join after %d passes (no lock?)", n_open, pass)); }
+            if (pass == 0) { n_rerun = n_open; }
+            const long long need2 = max_symbols_for(h->design, L);
+            if (h->seg_stride2 < need2) {
+                cudaFree(h->d_seg_dibits2); h->d_seg_dibits2 = nullptr; h->seg_stride2 = 0;
+                if (cudaMalloc(&h->d_seg_dibits2, C * (size_t)need2) != cudaSuccess) { return done(fail(TDM_ERR_NOMEM, "tdm_process_long: cudaMalloc failed")); }
+                h->seg_stride2 = need2;
+            }
+            tdm::launch_long_shift_states(h->d_states, d_final, S, st);      // every segment continues its predecessor
+            tdm::DemodParams q = p;
+            q.iq = d_iq + W; q.count = (int)L;
+            q.dibits = h->d_seg_dibits2; q.out_stride = h->seg_stride2; q.out_counts = d_counts2;
+            n = tdm::launch_demod(q, h->variant, st);
+            if (n < 0) { return done(fail(TDM_ERR_CUDA, "demod kernel launch failed: %s", cudaGetErrorString(cudaGetLastError()))); }
+            h->launches += n;
+            tdm::launch_stitch_adopt(h->d_seg_dibits, h->seg_stride, h->d_seg_dibits2, h->seg_stride2, d_counts, d_counts2, d_join, d_fixed, d_adopt,
+                                     d_final, h->d_states, S, need2, st);
+        }
+        // the logical channel continues from the run that produced the last segment's stream
+        if (cudaMemcpyAsync(h->d_states + (S - 1), d_final + (S - 1), sizeof(tdm_channel_state), cudaMemcpyDeviceToDevice, st) != cudaSuccess) {
+            return done(fail(TDM_ERR_CUDA, "tdm_process_long: state copy failed"));
+        }
+    }
+    tdm::launch_stitch_scan(d_counts, d_join, S, h->d_offs, st);
+    tdm::launch_stitch_copy(h->d_seg_dibits, h->seg_stride, d_counts, d_join, h->d_offs, d_out, dibits_cap, S, need, st);
+    // ---- the few samples the equal segments did not cover: sequentially, from the last segment's final state
+    if (tail > 0) {
+        tdm::DemodParams q = p;
+        q.n_channels = 1;
+        q.states = h->d_states + (S - 1);
+        q.iq = d_iq + covered; q.in_stride = tail; q.count = (int)tail;
+        q.dibits = h->d_seg_dibits; q.out_stride = h->seg_stride; q.out_counts = d_tailcount;
+        n = tdm::launch_demod(q, h->variant, st);
+        if (n < 0) { return done(fail(TDM_ERR_CUDA, "demod kernel launch failed: %s", cudaGetErrorString(cudaGetLastError()))); }
+        h->launches += n;
+        tdm::launch_stitch_append(h->d_seg_dibits, d_tailcount, h->d_offs + S, d_out, dibits_cap, max_symbols_for(h->design, tail), st);
+    }
+    // carry the logical channel's state to the next call
+    long long total = 0;
+    if (cudaMemcpyAsync(h->d_long_state, h->d_states + (S - 1), sizeof(tdm_channel_state), cudaMemcpyDeviceToDevice, st) != cudaSuccess ||
+        cudaMemcpyAsync(&total, h->d_offs + S, sizeof(long long), cudaMemcpyDeviceToHost, st) != cudaSuccess || cudaStreamSynchronize(st) != cudaSuccess) {
+        return done(fail(TDM_ERR_CUDA, "tdm_process_long: %s", cudaGetErrorString(cudaGetLastError())));
+    }
+    if (cudaGetLastError() != cudaSuccess) { return done(fail(TDM_ERR_CUDA, "tdm_process_long: kernel launch failed")); }
+    info->n_dibits = total; info->n_segments = S; info->n_rerun = n_rerun; info->segment_samples = (int32_t)L; info->warmup = (int32_t)W;
+    if (total > dibits_cap) { return done(fail(TDM_ERR_ARG, "tdm_process_long: %lld dibits do not fit into dibits_cap %lld (output truncated)", total, (long long)dibits_cap)); }
+    if (mem_kind == TDM_MEM_HOST) {
+        if (cudaMemcpy(dibits, d_tmp_out, (size_t)total, cudaMemcpyDeviceToHost) != cudaSuccess) { return done(fail(TDM_ERR_CUDA, "tdm_process_long: D2H copy failed")); }
+    }
+    return done(TDM_OK);
+}
+
 int tdm_get_state(tdm_handle* h, tdm_channel_state* host_states, int32_t n_channels) {
     if (!h || !host_states || n_channels != h->n_channels) { return fail(TDM_ERR_ARG, "tdm_get_state: bad arguments"); }
     DeviceGuard guard(h->device);
@@ -330,6 +485,14 @@ int tdm_reset_all(tdm_handle* h) {
     if (!h) { return fail(TDM_ERR_ARG, "null handle"); }
     std::vector<tdm_channel_state> st((size_t)h->n_channels);
     for (auto& s : st) { init_state(h->design, s); }
+    if (h->d_long_state) {
+        DeviceGuard guard(h->device);
+        tdm_channel_state two[2];
+        init_state(h->design, two[0]);
+        two[1] = two[0];
+        TDM_CUDA(cudaMemcpyAsync(h->d_long_state, two, sizeof(two), cudaMemcpyHostToDevice, h->stream));
+        TDM_CUDA(cudaStreamSynchronize(h->stream));
+    }
     return tdm_set_state(h, st.data(), h->n_channels);
 }
 

@@ -184,6 +184,29 @@ class Demodulator:
                                          stride, p(out.counts), flags, capi.TDM_MEM_DEVICE), "tdm_process")
         return out
 
+    def process_long(self, iq, warmup: int = 32768, out=None):
+        """ONE long capture of one channel ([N][2] float32, CUDA tensor or numpy array) demodulated as up to
+        n_channels overlapping time segments in parallel (tdm_process_long; decoded dibits only).
+        Returns (dibits [n] uint8 -- same kind of array as `iq` --, info dict)."""
+        info = capi.TdmLongInfo()
+        n = int(iq.shape[0])
+        cap = n // 2 + 64
+        if isinstance(iq, np.ndarray):
+            iq = np.ascontiguousarray(iq, dtype=np.float32)
+            dib = np.zeros(cap, np.uint8) if out is None else out
+            capi.check(self._lib.tdm_process_long(self._h, iq.ctypes.data_as(C.c_void_p), n, warmup, dib.ctypes.data_as(C.c_void_p),
+                                                  len(dib), C.byref(info), capi.TDM_MEM_HOST), "tdm_process_long")
+        else:
+            torch = _torch()
+            if not (iq.is_cuda and iq.dtype == torch.float32 and iq.dim() == 2 and iq.shape[1] == 2 and iq.is_contiguous()):
+                raise ValueError("iq must be a contiguous CUDA float32 tensor [N][2]")
+            self.set_stream(torch.cuda.current_stream(iq.device).cuda_stream)
+            dib = torch.empty(cap, dtype=torch.uint8, device=iq.device) if out is None else out
+            capi.check(self._lib.tdm_process_long(self._h, C.c_void_p(iq.data_ptr()), n, warmup, C.c_void_p(dib.data_ptr()),
+                                                  dib.numel(), C.byref(info), capi.TDM_MEM_DEVICE), "tdm_process_long")
+        d = {f: int(getattr(info, f)) for f, _ in capi.TdmLongInfo._fields_}
+        return dib[:d["n_dibits"]], d
+
     def pack_dibits(self, dibits, counts):
         """4 dibits per byte (first symbol in bits 7..6): the form shipped over NVLink by the multi-GPU gather."""
         torch = _torch()
