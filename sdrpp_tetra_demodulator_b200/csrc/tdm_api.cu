@@ -331,7 +331,12 @@ int tdm_process_long(tdm_handle* h, const float* iq, int64_t n_samples, int32_t 
     if (n_samples == 0) { return TDM_OK; }
     DeviceGuard guard(h->device);
     cudaStream_t st = h->stream;
-    const int K = 128;                                          // dibits that must agree at a join (2^-256 for a chance match)
+    // dibits that must agree at a join.  128 would do to identify the place (2^-256 for a chance match), but a chain that
+    // has only just locked still makes a stray decision error every few hundred symbols for a few thousand symbols
+    // more (measured: 60 of 4096 segments at 1e9 samples with K = 128): demanding W/8 (up to 4096) error-free
+    // symbols before the hand-over sends those segments to the sequential redo instead.
+    int K = warmup / 8;
+    K = K < 128 ? 128 : (K > 4096 ? 4096 : K);
     // segments: S rows of L + W samples, row c starts at sample c L; a segment must dwarf its warm-up to be worth it
     int S = h->n_channels;
     const long long min_seg = 4LL * warmup;

@@ -184,7 +184,7 @@ class Demodulator:
                                          stride, p(out.counts), flags, capi.TDM_MEM_DEVICE), "tdm_process")
         return out
 
-    def process_long(self, iq, warmup: int = 32768, out=None):
+    def process_long(self, iq, warmup: int = 65536, out=None):
         """ONE long capture of one channel ([N][2] float32, CUDA tensor or numpy array) demodulated as up to
         n_channels overlapping time segments in parallel (tdm_process_long; decoded dibits only).
         Returns (dibits [n] uint8 -- same kind of array as `iq` --, info dict)."""

@@ -2,7 +2,7 @@
 """bench_long.py -- BASELINE.json configs[1]: "1 channel, 1e9 complex samples on a single B200, fused kernel vs CPU
 reference", through tdm_process_long (time-segment parallelism).
 
-    python tools/bench_long.py [--samples 1000000000] [--segments 4096] [--warmup 32768] [--steps 3] [--warmup-steps 1]
+    python tools/bench_long.py [--samples 1000000000] [--segments 4096] [--warmup 65536] [--steps 3] [--warmup-steps 1]
 
 One step = the whole capture (8 GB of IQ resident in HBM) through tdm_process_long, loop state carried from the
 previous step.  Beside it: the same chain walked sequentially on the GPU (one channel = one lane of one warp: the
@@ -26,7 +26,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--samples", type=int, default=1_000_000_000)
     ap.add_argument("--segments", type=int, default=4096)
-    ap.add_argument("--warmup", type=int, default=32768)
+    ap.add_argument("--warmup", type=int, default=65536)
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup-steps", type=int, default=1)
     ap.add_argument("--no-cpu-baseline", action="store_true")
