@@ -186,7 +186,8 @@ int tdm_process(tdm_handle* h, const float* iq, int64_t in_stride, int32_t count
  *
  * CONTRACT: decoded dibits only.  They equal the sequential chain's (tdm_process on one channel, hence the
  * reference's) from the point where the sequential chain has locked; before that, and in the float loop states,
- * the two may differ.  iq: [n_samples] interleaved float pairs; dibits: [dibits_cap] bytes, info->n_dibits
+ * the two may differ; across a stretch without signal (neither run locks) the streams are joined at the nominal
+ * place and may gain or lose a symbol (info->n_forced).  iq: [n_samples] interleaved float pairs; dibits: [dibits_cap] bytes, info->n_dibits
  * written; n_samples / 2 + 64 is always enough.  Uses the handle's per-channel states as scratch: do not mix with
  * tdm_process on the same handle. */
 typedef struct tdm_long_info {
@@ -195,6 +196,9 @@ typedef struct tdm_long_info {
     int32_t n_rerun;           /* segments that had to be redone sequentially (join not found)    */
     int32_t segment_samples;   /* L                                                               */
     int32_t warmup;            /* W actually used (0 when a single segment was enough)            */
+    int32_t n_forced;          /* segments joined at the nominal place: predecessor not locked there (no signal),
+                                  or its continuation contradicted by two independent later runs             */
+    int32_t reserved;
 } tdm_long_info;
 int tdm_process_long(tdm_handle* h, const float* iq, int64_t n_samples, int32_t warmup, uint8_t* dibits, int64_t dibits_cap,
                      tdm_long_info* info, int32_t mem_kind);

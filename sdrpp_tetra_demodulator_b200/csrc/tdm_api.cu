@@ -83,7 +83,7 @@ struct tdm_handle {
     uint8_t* d_seg_dibits = nullptr;
     uint8_t* d_seg_dibits2 = nullptr;
     long long seg_stride = 0, seg_stride2 = 0;
-    int* d_seg_ints = nullptr;                   // counts[S], counts2[S], join[S], fixed[S], adopt[S], n_open, tail count
+    int* d_seg_ints = nullptr;                   // counts[S], counts2[S], join[S], fixed[S], adopt[S], n_open, tail count, n_forced
     long long* d_offs = nullptr;                 // [S + 1]
 };
 
@@ -359,7 +359,7 @@ int tdm_process_long(tdm_handle* h, const float* iq, int64_t n_samples, int32_t 
     }
     const size_t C = (size_t)h->n_channels;
     if (!h->d_states2) { TDM_CUDA(cudaMalloc(&h->d_states2, sizeof(tdm_channel_state) * C)); }
-    if (!h->d_seg_ints) { TDM_CUDA(cudaMalloc(&h->d_seg_ints, sizeof(int) * (5 * C + 2))); }
+    if (!h->d_seg_ints) { TDM_CUDA(cudaMalloc(&h->d_seg_ints, sizeof(int) * (7 * C + 3))); }
     if (!h->d_offs) { TDM_CUDA(cudaMalloc(&h->d_offs, sizeof(long long) * (C + 1))); }
     if (h->seg_stride < need) {
         cudaFree(h->d_seg_dibits); h->d_seg_dibits = nullptr; h->seg_stride = 0;
@@ -373,6 +373,9 @@ int tdm_process_long(tdm_handle* h, const float* iq, int64_t n_samples, int32_t 
     int* d_adopt = d_fixed + C;
     int* d_nopen = d_adopt + C;
     int* d_tailcount = d_nopen + 1;
+    int* d_nforced = d_tailcount + 1;
+    int* d_agree = d_nforced + 1;
+    int* d_mode = d_agree + C;
 
     const float2* d_iq = reinterpret_cast<const float2*>(iq);
     float2* d_tmp_iq = nullptr;
@@ -405,20 +408,22 @@ int tdm_process_long(tdm_handle* h, const float* iq, int64_t n_samples, int32_t 
     const int mid = (int)(W / 2);
     int n_rerun = 0;
     if (S > 1) {
-        if (cudaMemsetAsync(d_fixed, 0, sizeof(int) * (size_t)S, st) != cudaSuccess ||
+        if (cudaMemsetAsync(d_fixed, 0, sizeof(int) * (size_t)S, st) != cudaSuccess || cudaMemsetAsync(d_nforced, 0, sizeof(int), st) != cudaSuccess ||
             cudaMemcpyAsync(h->d_states2, h->d_states, sizeof(tdm_channel_state) * (size_t)S, cudaMemcpyDeviceToDevice, st) != cudaSuccess) {
             return done(fail(TDM_ERR_CUDA, "tdm_process_long: %s", cudaGetErrorString(cudaGetLastError())));
         }
         tdm_channel_state* d_final = h->d_states2;                     // final loop state of the run whose stream each segment uses
         for (int pass = 0;; ++pass) {
             tdm::launch_stitch_find(h->d_seg_dibits, h->seg_stride, d_counts, S, K, mid - 2048, mid + 256, d_join, d_fixed, st);
-            tdm::launch_stitch_plan(d_join, d_fixed, S, d_adopt, d_nopen, st);
+            // A segment whose predecessor is not locked at the boundary (no signal there) is joined at the nominal place
+            // right away; the pass limit only guards against pathological inputs.
+            const bool give_up = pass >= 64;
+            tdm::launch_stitch_plan(d_join, d_fixed, d_counts, S, d_adopt, d_nopen, d_nforced, mid, give_up ? 1 : 0, d_final, st);
             int n_open = 0;
             if (cudaMemcpyAsync(&n_open, d_nopen, sizeof(int), cudaMemcpyDeviceToHost, st) != cudaSuccess || cudaStreamSynchronize(st) != cudaSuccess) {
                 return done(fail(TDM_ERR_CUDA, "tdm_process_long: %s", cudaGetErrorString(cudaGetLastError())));
             }
             if (n_open == 0) { break; }
-            if (pass >= 64) { return done(fail(TDM_ERR_UNSUPPORTED, "tdm_process_long: %d segments still do not join after %d passes (no lock?)", n_open, pass)); }
             if (pass == 0) { n_rerun = n_open; }
             const long long need2 = max_symbols_for(h->design, L);
             if (h->seg_stride2 < need2) {
@@ -434,10 +439,11 @@ int tdm_process_long(tdm_handle* h, const float* iq, int64_t n_samples, int32_t 
             if (n < 0) { return done(fail(TDM_ERR_CUDA, "demod kernel launch failed: %s", cudaGetErrorString(cudaGetLastError()))); }
             h->launches += n;
             tdm::launch_stitch_adopt(h->d_seg_dibits, h->seg_stride, h->d_seg_dibits2, h->seg_stride2, d_counts, d_counts2, d_join, d_fixed, d_adopt,
-                                     d_final, h->d_states, S, need2, st);
+                                     d_agree, d_mode, d_nforced, mid, K < 512 ? K : 512, d_final, h->d_states, S, need2, st);
         }
         // the logical channel continues from the run that produced the last segment's stream
-        if (cudaMemcpyAsync(h->d_states + (S - 1), d_final + (S - 1), sizeof(tdm_channel_state), cudaMemcpyDeviceToDevice, st) != cudaSuccess) {
+        if (cudaMemcpyAsync(&info->n_forced, d_nforced, sizeof(int), cudaMemcpyDeviceToHost, st) != cudaSuccess ||
+            cudaMemcpyAsync(h->d_states + (S - 1), d_final + (S - 1), sizeof(tdm_channel_state), cudaMemcpyDeviceToDevice, st) != cudaSuccess) {
             return done(fail(TDM_ERR_CUDA, "tdm_process_long: state copy failed"));
         }
     }

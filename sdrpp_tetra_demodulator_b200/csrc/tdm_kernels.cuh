@@ -55,10 +55,11 @@ void launch_long_init_states(tdm_channel_state* states, const tdm_channel_state*
 void launch_long_shift_states(tdm_channel_state* dst, const tdm_channel_state* src, int n, cudaStream_t s);
 void launch_stitch_find(const uint8_t* dib, long long stride, const int* counts, int n_rows, int K, int jlo, int jhi, int* join,
                         const int* fixed, cudaStream_t s);
-void launch_stitch_plan(const int* join, const int* fixed, int n_rows, int* adopt, int* n_open, cudaStream_t s);
+void launch_stitch_plan(int* join, int* fixed, const int* counts, int n_rows, int* adopt, int* n_open, int* n_forced, int force_at,
+                        int force_all, const tdm_channel_state* final_states, cudaStream_t s);
 void launch_stitch_adopt(uint8_t* dib, long long stride, const uint8_t* dib2, long long stride2, int* counts, const int* counts2, int* join,
-                         int* fixed, const int* adopt, tdm_channel_state* final_states, const tdm_channel_state* run_states, int n_rows,
-                         long long max_len, cudaStream_t s);
+                         int* fixed, const int* adopt, int* agree, int* mode, int* n_forced, int force_at, int K,
+                         tdm_channel_state* final_states, const tdm_channel_state* run_states, int n_rows, long long max_len, cudaStream_t s);
 void launch_stitch_scan(const int* counts, const int* join, int n_rows, long long* offs, cudaStream_t s);
 void launch_stitch_copy(const uint8_t* dib, long long stride, const int* counts, const int* join, const long long* offs, uint8_t* out,
                         long long cap, int n_rows, long long max_len, cudaStream_t s);

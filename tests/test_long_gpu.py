@@ -105,6 +105,34 @@ def test_consecutive_calls_continue_one_stream(O, pkg, torch_cuda):
     assert np.array_equal(got[100_000:n], seq[100_000:n])
 
 
+def test_stretch_without_signal(O, pkg, torch_cuda):
+    """a dead stretch several segments long: a run that ends inside it is not locked (DQPSKSymbolExtractor::sync down),
+    so there is nothing for its successor to agree with and the join is made at the nominal place.  Before the gap the
+    stream equals the sequential one exactly; after it, once both have locked again, up to the few symbols the gap
+    may have gained or lost"""
+    torch = torch_cuda
+    N = 2_400_000
+    iq = O.generate(1, N)[0].copy()
+    rng = np.random.default_rng(1)
+    iq[500_000:1_500_000] = (1e-4 * rng.standard_normal((1_000_000, 2))).astype(np.float32)
+    seq = _sequential(O, iq)
+    with pkg.Demodulator(16, 1024) as dm:
+        got, info = dm.process_long(torch.from_numpy(iq).cuda(), warmup=40_000)
+        torch.cuda.synchronize()
+        got = got.cpu().numpy()
+    assert info["n_segments"] >= 12 and info["n_forced"] >= 3, info
+    # without signal the timing loop free-runs (omega wanders inside its +-2 % limits), so how many garbage symbols a
+    # run emits across the gap is its own business: the two streams may differ by a fraction of a percent of the gap
+    assert abs(len(got) - len(seq)) <= 5000, (len(got), len(seq), info)
+    assert np.array_equal(got[100_000:240_000], seq[100_000:240_000])
+    # after the gap, once both have locked again: identical.  Both streams end at the capture's last sample, so they
+    # are compared aligned at the END (give or take the symbol that can fall either side of it)
+    tail = 150_000
+    ref = seq[len(seq) - tail - 4:len(seq) - 4]
+    best = min(int((got[len(got) - tail - 4 - d:len(got) - 4 - d] != ref).sum()) for d in range(-3, 4))
+    assert best == 0, best
+
+
 def test_argument_checks(pkg, torch_cuda):
     torch = torch_cuda
     with pkg.Demodulator(4, 1024) as dm:
