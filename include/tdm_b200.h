@@ -202,6 +202,15 @@ typedef struct tdm_long_info {
 } tdm_long_info;
 int tdm_process_long(tdm_handle* h, const float* iq, int64_t n_samples, int32_t warmup, uint8_t* dibits, int64_t dibits_cap,
                      tdm_long_info* info, int32_t mem_kind);
+/* The same for n_channels long captures at once (BASELINE.json configs[2], "256 channels x 4e6 samples"): every channel
+ * is cut into floor(handle rows / n_channels) segments, so a few hundred channels fill the GPU like a few thousand do.
+ *   iq         : [n_channels][in_stride] float pairs, n_samples used per channel
+ *   dibits     : [n_channels][out_stride] bytes; out_counts [n_channels] int64 dibits written per channel
+ *                (host or device pointers according to mem_kind); n_samples / 2 + 64 is always a sufficient out_stride
+ *   info       : n_dibits = sum over channels; n_segments = segments per channel
+ * Carried state is per channel; calling with a different n_channels than last time starts every channel from reset. */
+int tdm_process_long_batch(tdm_handle* h, const float* iq, int64_t in_stride, int64_t n_samples, int32_t n_channels, int32_t warmup,
+                           uint8_t* dibits, int64_t out_stride, int64_t* out_counts, tdm_long_info* info, int32_t mem_kind);
 
 /* PI4DQPSK::reset (src/dsp/pi4dqpsk.cpp:120-130): loop scalars back to their
  * initial values, RRC history cleared, FLL/timing histories KEPT (fll.cpp:120-127,

@@ -40,7 +40,7 @@ EXPORTED_SYMBOLS = [
     "tdm_max_symbols", "tdm_process", "tdm_reset", "tdm_reset_all", "tdm_get_state", "tdm_set_state",
     "tdm_get_metrics", "tdm_set_config", "tdm_get_design", "tdm_set_kernel_variant", "tdm_last_kernel_ms",
     "tdm_launch_count", "tdm_pack_dibits", "tdm_synth_capture", "tdm_last_error", "tdm_abi_version",
-    "tdm_process_long",
+    "tdm_process_long", "tdm_process_long_batch",
 ]
 # ... and include/tdm_burst_b200.h
 EXPORTED_BURST_SYMBOLS = [
@@ -164,6 +164,7 @@ def lib() -> C.CDLL:
         "tdm_last_error": (C.c_char_p, []),
         "tdm_abi_version": (C.c_int, []),
         "tdm_process_long": (C.c_int, [vp, vp, i64, i32, vp, i64, C.POINTER(TdmLongInfo), i32]),
+        "tdm_process_long_batch": (C.c_int, [vp, vp, i64, i64, i32, i32, vp, i64, vp, C.POINTER(TdmLongInfo), i32]),
         "tdm_bsync_create": (C.c_int, [i32, i64, i32, C.POINTER(vp)]),
         "tdm_bsync_destroy": (C.c_int, [vp]),
         "tdm_bsync_set_stream": (C.c_int, [vp, vp]),

@@ -78,13 +78,14 @@ struct tdm_handle {
     uint8_t* d_bits = nullptr;
     int* d_counts = nullptr;
     // tdm_process_long: the logical channel's carried state [0] + a freshly initialised state [1]; per-segment scratch
-    tdm_channel_state* d_long_state = nullptr;
+    tdm_channel_state* d_long_state = nullptr;   // [n_channels + 1]: carried state per logical channel, then one fresh state
+    int long_channels = 0;                       // logical channels of the previous tdm_process_long_batch call
     tdm_channel_state* d_states2 = nullptr;
     uint8_t* d_seg_dibits = nullptr;
     uint8_t* d_seg_dibits2 = nullptr;
     long long seg_stride = 0, seg_stride2 = 0;
     int* d_seg_ints = nullptr;                   // counts[S], counts2[S], join[S], fixed[S], adopt[S], n_open, tail count, n_forced
-    long long* d_offs = nullptr;                 // [S + 1]
+    long long* d_offs = nullptr;                 // [rows] offsets, then [rows] per-channel totals
 };
 
 namespace {
@@ -102,6 +103,8 @@ void fill_params(const tdm_handle* h, tdm::DemodParams& p) {
     p.bank = h->d_bank;
     p.n_channels = h->n_channels;
     p.states = h->d_states;
+    p.rows_per_channel = 1;
+    p.channel_stride = 0;
 }
 
 void init_state(const tdm_design& d, tdm_channel_state& s) {
@@ -321,85 +324,102 @@ int tdm_process(tdm_handle* h, const float* iq, int64_t in_stride, int32_t count
 }
 
 // SURVEY.md 8f rank 4.  See tdm_stitch.cu for the scheme and include/tdm_b200.h for the contract.
-int tdm_process_long(tdm_handle* h, const float* iq, int64_t n_samples, int32_t warmup, uint8_t* dibits, int64_t dibits_cap,
-                     tdm_long_info* info, int32_t mem_kind) {
+int tdm_process_long_batch(tdm_handle* h, const float* iq, int64_t in_stride, int64_t n_samples, int32_t n_channels, int32_t warmup,
+                           uint8_t* dibits, int64_t out_stride, int64_t* out_counts, tdm_long_info* info, int32_t mem_kind) {
     if (!h || !info) { return fail(TDM_ERR_ARG, "tdm_process_long: null handle / info"); }
     std::memset(info, 0, sizeof(*info));
-    if (n_samples < 0 || (n_samples > 0 && (!iq || !dibits)) || dibits_cap < 0) { return fail(TDM_ERR_ARG, "tdm_process_long: bad buffers"); }
+    if (n_channels < 1 || n_channels > h->n_channels) { return fail(TDM_ERR_ARG, "tdm_process_long: n_channels must be 1..%d (the handle's rows)", h->n_channels); }
+    if (n_samples < 0 || in_stride < n_samples || out_stride < 0 || !out_counts || (n_samples > 0 && (!iq || !dibits))) { return fail(TDM_ERR_ARG, "tdm_process_long: bad buffers"); }
     if (warmup < 1024 || warmup > (1 << 24)) { return fail(TDM_ERR_ARG, "tdm_process_long: warmup must be 1024..2^24 samples"); }
     if (mem_kind != TDM_MEM_HOST && mem_kind != TDM_MEM_DEVICE) { return fail(TDM_ERR_ARG, "tdm_process_long: mem_kind"); }
-    if (n_samples == 0) { return TDM_OK; }
     DeviceGuard guard(h->device);
     cudaStream_t st = h->stream;
+    const int C = n_channels;
+    if (n_samples == 0) {
+        if (mem_kind == TDM_MEM_HOST) { for (int c = 0; c < C; ++c) { out_counts[c] = 0; } }
+        else { TDM_CUDA(cudaMemsetAsync(out_counts, 0, sizeof(int64_t) * (size_t)C, st)); }
+        return TDM_OK;
+    }
     // dibits that must agree at a join.  128 would do to identify the place (2^-256 for a chance match), but a chain that
     // has only just locked still makes a stray decision error every few hundred symbols for a few thousand symbols
     // more (measured: 60 of 4096 segments at 1e9 samples with K = 128): demanding W/8 (up to 4096) error-free
     // symbols before the hand-over sends those segments to the sequential redo instead.
     int K = warmup / 8;
     K = K < 128 ? 128 : (K > 4096 ? 4096 : K);
-    // segments: S rows of L + W samples, row c starts at sample c L; a segment must dwarf its warm-up to be worth it
-    int S = h->n_channels;
+    // S segments per channel: rows of L + W samples, segment s starts at sample s L; a segment must dwarf its warm-up
+    int S = h->n_channels / C;
     const long long min_seg = 4LL * warmup;
     if ((n_samples - warmup) / S < min_seg) { S = (int)((n_samples - warmup) / min_seg); }
     if (S < 1) { S = 1; }
-    long long L = (S > 1) ? (((n_samples - warmup) / S) & ~7LL) : n_samples;
+    const long long L = (S > 1) ? (((n_samples - warmup) / S) & ~7LL) : n_samples;
     const long long W = (S > 1) ? warmup : 0;
-    if (L + W > 0x7fffffffLL) { return fail(TDM_ERR_ARG, "tdm_process_long: segments of %lld samples exceed the 32-bit count of a launch; use more segments", L + W); }
+    if (L + W > 0x7fffffffLL) { return fail(TDM_ERR_ARG, "tdm_process_long: segments of %lld samples exceed the 32-bit count of a launch; use more rows", L + W); }
     const long long covered = (S > 1) ? S * L + W : n_samples;
-    const long long tail = n_samples - covered;                 // < 8 S + S samples, demodulated sequentially at the end
+    const long long tail = n_samples - covered;                 // < 9 S samples per channel, demodulated sequentially at the end
     const long long need = max_symbols_for(h->design, L + W);
+    const int R = C * S;
 
-    // scratch
-    if (!h->d_long_state) {
-        TDM_CUDA(cudaMalloc(&h->d_long_state, 2 * sizeof(tdm_channel_state)));
-        tdm_channel_state two[2];
-        init_state(h->design, two[0]);
-        two[1] = two[0];
-        TDM_CUDA(cudaMemcpyAsync(h->d_long_state, two, sizeof(two), cudaMemcpyHostToDevice, st));
+    // scratch (sized for the handle's rows once)
+    const size_t HR = (size_t)h->n_channels;
+    if (!h->d_long_state) { TDM_CUDA(cudaMalloc(&h->d_long_state, (HR + 1) * sizeof(tdm_channel_state))); }
+    if (h->long_channels != C) {                                // first use, after tdm_reset_all, or a different channel count: start from reset
+        std::vector<tdm_channel_state> init((size_t)C + 1);
+        for (auto& s : init) { init_state(h->design, s); }
+        TDM_CUDA(cudaMemcpyAsync(h->d_long_state, init.data(), sizeof(tdm_channel_state) * init.size(), cudaMemcpyHostToDevice, st));
+        TDM_CUDA(cudaStreamSynchronize(st));
+        h->long_channels = C;
     }
-    const size_t C = (size_t)h->n_channels;
-    if (!h->d_states2) { TDM_CUDA(cudaMalloc(&h->d_states2, sizeof(tdm_channel_state) * C)); }
-    if (!h->d_seg_ints) { TDM_CUDA(cudaMalloc(&h->d_seg_ints, sizeof(int) * (7 * C + 3))); }
-    if (!h->d_offs) { TDM_CUDA(cudaMalloc(&h->d_offs, sizeof(long long) * (C + 1))); }
+    tdm_channel_state* d_carried = h->d_long_state;
+    tdm_channel_state* d_fresh = h->d_long_state + C;
+    if (!h->d_states2) { TDM_CUDA(cudaMalloc(&h->d_states2, sizeof(tdm_channel_state) * HR)); }
+    if (!h->d_seg_ints) { TDM_CUDA(cudaMalloc(&h->d_seg_ints, sizeof(int) * (8 * HR + 4))); }
+    if (!h->d_offs) { TDM_CUDA(cudaMalloc(&h->d_offs, sizeof(long long) * (2 * HR + 2))); }
     if (h->seg_stride < need) {
         cudaFree(h->d_seg_dibits); h->d_seg_dibits = nullptr; h->seg_stride = 0;
-        TDM_CUDA(cudaMalloc(&h->d_seg_dibits, C * (size_t)need));
+        TDM_CUDA(cudaMalloc(&h->d_seg_dibits, HR * (size_t)need));
         h->seg_stride = need;
     }
     int* d_counts = h->d_seg_ints;
-    int* d_counts2 = d_counts + C;
-    int* d_join = d_counts2 + C;
-    int* d_fixed = d_join + C;
-    int* d_adopt = d_fixed + C;
-    int* d_nopen = d_adopt + C;
-    int* d_tailcount = d_nopen + 1;
-    int* d_nforced = d_tailcount + 1;
-    int* d_agree = d_nforced + 1;
-    int* d_mode = d_agree + C;
+    int* d_counts2 = d_counts + HR;
+    int* d_join = d_counts2 + HR;
+    int* d_fixed = d_join + HR;
+    int* d_adopt = d_fixed + HR;
+    int* d_agree = d_adopt + HR;
+    int* d_mode = d_agree + HR;
+    int* d_tailcount = d_mode + HR;                              // [C]
+    int* d_nopen = d_tailcount + HR;
+    int* d_nforced = d_nopen + 1;
+    long long* d_offs = h->d_offs;
+    long long* d_totals = h->d_offs + HR;
 
     const float2* d_iq = reinterpret_cast<const float2*>(iq);
+    long long ch_stride = in_stride;
     float2* d_tmp_iq = nullptr;
     uint8_t* d_out = dibits;
     uint8_t* d_tmp_out = nullptr;
-    auto done = [&](int code) { cudaFree(d_tmp_iq); cudaFree(d_tmp_out); return code; };
+    long long* d_tmp_counts = nullptr;
+    auto done = [&](int code) { cudaFree(d_tmp_iq); cudaFree(d_tmp_out); cudaFree(d_tmp_counts); return code; };
     if (mem_kind == TDM_MEM_HOST) {
-        if (cudaMalloc(&d_tmp_iq, sizeof(float2) * (size_t)n_samples) != cudaSuccess || cudaMalloc(&d_tmp_out, (size_t)(dibits_cap > 0 ? dibits_cap : 1)) != cudaSuccess) {
-            return done(fail(TDM_ERR_NOMEM, "tdm_process_long: cannot stage %lld samples on the device", (long long)n_samples));
+        if (cudaMalloc(&d_tmp_iq, sizeof(float2) * (size_t)n_samples * (size_t)C) != cudaSuccess ||
+            cudaMalloc(&d_tmp_out, (size_t)C * (size_t)(out_stride > 0 ? out_stride : 1)) != cudaSuccess) {
+            return done(fail(TDM_ERR_NOMEM, "tdm_process_long: cannot stage %d x %lld samples on the device", C, (long long)n_samples));
         }
-        if (cudaMemcpyAsync(d_tmp_iq, iq, sizeof(float2) * (size_t)n_samples, cudaMemcpyHostToDevice, st) != cudaSuccess) {
+        if (cudaMemcpy2DAsync(d_tmp_iq, sizeof(float2) * (size_t)n_samples, iq, sizeof(float2) * (size_t)in_stride, sizeof(float2) * (size_t)n_samples,
+                              (size_t)C, cudaMemcpyHostToDevice, st) != cudaSuccess) {
             return done(fail(TDM_ERR_CUDA, "tdm_process_long: H2D copy failed"));
         }
-        d_iq = d_tmp_iq;
+        d_iq = d_tmp_iq; ch_stride = n_samples;
         d_out = d_tmp_out;
     }
 
     tdm::DemodParams p;
     fill_params(h, p);
-    p.n_channels = S;
+    p.n_channels = R;
     p.syms = nullptr; p.bits = nullptr; p.accumulate = 0;
-    // ---- pass 1: all segments at once, segment 0 from the carried state, the others from reset state
-    tdm::launch_long_init_states(h->d_states, h->d_long_state, h->d_long_state + 1, S, st);
-    p.iq = d_iq; p.in_stride = L; p.count = (int)(L + W);
+    p.rows_per_channel = S; p.channel_stride = ch_stride;
+    // ---- pass 1: all segments at once, the first of every channel from its carried state, the others from reset state
+    tdm::launch_long_init_states(h->d_states, d_carried, d_fresh, R, S, st);
+    p.iq = d_iq; p.in_stride = (S > 1) ? L : ch_stride; p.count = (int)(L + W);
     p.dibits = h->d_seg_dibits; p.out_stride = h->seg_stride; p.out_counts = d_counts;
     int n = tdm::launch_demod(p, h->variant, st);
     if (n < 0) { return done(fail(TDM_ERR_CUDA, "demod kernel launch failed: %s", cudaGetErrorString(cudaGetLastError()))); }
@@ -408,17 +428,17 @@ int tdm_process_long(tdm_handle* h, const float* iq, int64_t n_samples, int32_t 
     const int mid = (int)(W / 2);
     int n_rerun = 0;
     if (S > 1) {
-        if (cudaMemsetAsync(d_fixed, 0, sizeof(int) * (size_t)S, st) != cudaSuccess || cudaMemsetAsync(d_nforced, 0, sizeof(int), st) != cudaSuccess ||
-            cudaMemcpyAsync(h->d_states2, h->d_states, sizeof(tdm_channel_state) * (size_t)S, cudaMemcpyDeviceToDevice, st) != cudaSuccess) {
+        if (cudaMemsetAsync(d_fixed, 0, sizeof(int) * (size_t)R, st) != cudaSuccess || cudaMemsetAsync(d_nforced, 0, sizeof(int), st) != cudaSuccess ||
+            cudaMemcpyAsync(h->d_states2, h->d_states, sizeof(tdm_channel_state) * (size_t)R, cudaMemcpyDeviceToDevice, st) != cudaSuccess) {
             return done(fail(TDM_ERR_CUDA, "tdm_process_long: %s", cudaGetErrorString(cudaGetLastError())));
         }
         tdm_channel_state* d_final = h->d_states2;                     // final loop state of the run whose stream each segment uses
         for (int pass = 0;; ++pass) {
-            tdm::launch_stitch_find(h->d_seg_dibits, h->seg_stride, d_counts, S, K, mid - 2048, mid + 256, d_join, d_fixed, st);
+            tdm::launch_stitch_find(h->d_seg_dibits, h->seg_stride, d_counts, R, S, K, mid - 2048, mid + 256, d_join, d_fixed, st);
             // A segment whose predecessor is not locked at the boundary (no signal there) is joined at the nominal place
             // right away; the pass limit only guards against pathological inputs.
             const bool give_up = pass >= 64;
-            tdm::launch_stitch_plan(d_join, d_fixed, d_counts, S, d_adopt, d_nopen, d_nforced, mid, give_up ? 1 : 0, d_final, st);
+            tdm::launch_stitch_plan(d_join, d_fixed, d_counts, R, S, d_adopt, d_nopen, d_nforced, mid, give_up ? 1 : 0, d_final, st);
             int n_open = 0;
             if (cudaMemcpyAsync(&n_open, d_nopen, sizeof(int), cudaMemcpyDeviceToHost, st) != cudaSuccess || cudaStreamSynchronize(st) != cudaSuccess) {
                 return done(fail(TDM_ERR_CUDA, "tdm_process_long: %s", cudaGetErrorString(cudaGetLastError())));
@@ -428,10 +448,10 @@ int tdm_process_long(tdm_handle* h, const float* iq, int64_t n_samples, int32_t 
             const long long need2 = max_symbols_for(h->design, L);
             if (h->seg_stride2 < need2) {
                 cudaFree(h->d_seg_dibits2); h->d_seg_dibits2 = nullptr; h->seg_stride2 = 0;
-                if (cudaMalloc(&h->d_seg_dibits2, C * (size_t)need2) != cudaSuccess) { return done(fail(TDM_ERR_NOMEM, "tdm_process_long: cudaMalloc failed")); }
+                if (cudaMalloc(&h->d_seg_dibits2, HR * (size_t)need2) != cudaSuccess) { return done(fail(TDM_ERR_NOMEM, "tdm_process_long: cudaMalloc failed")); }
                 h->seg_stride2 = need2;
             }
-            tdm::launch_long_shift_states(h->d_states, d_final, S, st);      // every segment continues its predecessor
+            tdm::launch_long_shift_states(h->d_states, d_final, R, S, st);   // every segment continues its predecessor
             tdm::DemodParams q = p;
             q.iq = d_iq + W; q.count = (int)L;
             q.dibits = h->d_seg_dibits2; q.out_stride = h->seg_stride2; q.out_counts = d_counts2;
@@ -439,41 +459,68 @@ int tdm_process_long(tdm_handle* h, const float* iq, int64_t n_samples, int32_t 
             if (n < 0) { return done(fail(TDM_ERR_CUDA, "demod kernel launch failed: %s", cudaGetErrorString(cudaGetLastError()))); }
             h->launches += n;
             tdm::launch_stitch_adopt(h->d_seg_dibits, h->seg_stride, h->d_seg_dibits2, h->seg_stride2, d_counts, d_counts2, d_join, d_fixed, d_adopt,
-                                     d_agree, d_mode, d_nforced, mid, K < 512 ? K : 512, d_final, h->d_states, S, need2, st);
+                                     d_agree, d_mode, d_nforced, mid, K < 512 ? K : 512, d_final, h->d_states, R, S, need2, st);
         }
-        // the logical channel continues from the run that produced the last segment's stream
-        if (cudaMemcpyAsync(&info->n_forced, d_nforced, sizeof(int), cudaMemcpyDeviceToHost, st) != cudaSuccess ||
-            cudaMemcpyAsync(h->d_states + (S - 1), d_final + (S - 1), sizeof(tdm_channel_state), cudaMemcpyDeviceToDevice, st) != cudaSuccess) {
-            return done(fail(TDM_ERR_CUDA, "tdm_process_long: state copy failed"));
+        // every logical channel continues from the run that produced its last segment's stream
+        if (cudaMemcpyAsync(&info->n_forced, d_nforced, sizeof(int), cudaMemcpyDeviceToHost, st) != cudaSuccess) {
+            return done(fail(TDM_ERR_CUDA, "tdm_process_long: copy failed"));
         }
+        tdm::launch_long_last_states(d_carried, d_final, C, S, 0, st);
+    } else {
+        tdm::launch_long_last_states(d_carried, h->d_states, C, 1, 0, st);
     }
-    tdm::launch_stitch_scan(d_counts, d_join, S, h->d_offs, st);
-    tdm::launch_stitch_copy(h->d_seg_dibits, h->seg_stride, d_counts, d_join, h->d_offs, d_out, dibits_cap, S, need, st);
-    // ---- the few samples the equal segments did not cover: sequentially, from the last segment's final state
+    tdm::launch_stitch_scan(d_counts, d_join, R, S, d_offs, d_totals, st);
+    tdm::launch_stitch_copy(h->d_seg_dibits, h->seg_stride, d_counts, d_join, d_offs, S, d_out, out_stride, R, need, st);
+    // ---- the few samples the equal segments did not cover: sequentially, every channel from its last state (now in d_carried)
     if (tail > 0) {
         tdm::DemodParams q = p;
-        q.n_channels = 1;
-        q.states = h->d_states + (S - 1);
-        q.iq = d_iq + covered; q.in_stride = tail; q.count = (int)tail;
+        q.n_channels = C; q.rows_per_channel = 1; q.channel_stride = 0;
+        q.states = d_carried;
+        q.iq = d_iq + covered; q.in_stride = ch_stride; q.count = (int)tail;
         q.dibits = h->d_seg_dibits; q.out_stride = h->seg_stride; q.out_counts = d_tailcount;
         n = tdm::launch_demod(q, h->variant, st);
         if (n < 0) { return done(fail(TDM_ERR_CUDA, "demod kernel launch failed: %s", cudaGetErrorString(cudaGetLastError()))); }
         h->launches += n;
-        tdm::launch_stitch_append(h->d_seg_dibits, d_tailcount, h->d_offs + S, d_out, dibits_cap, max_symbols_for(h->design, tail), st);
+        tdm::launch_stitch_append(h->d_seg_dibits, h->seg_stride, d_tailcount, d_totals, d_out, out_stride, C, max_symbols_for(h->design, tail), st);
     }
-    // carry the logical channel's state to the next call
-    long long total = 0;
-    if (cudaMemcpyAsync(h->d_long_state, h->d_states + (S - 1), sizeof(tdm_channel_state), cudaMemcpyDeviceToDevice, st) != cudaSuccess ||
-        cudaMemcpyAsync(&total, h->d_offs + S, sizeof(long long), cudaMemcpyDeviceToHost, st) != cudaSuccess || cudaStreamSynchronize(st) != cudaSuccess) {
+    std::vector<long long> totals((size_t)C);
+    if (cudaMemcpyAsync(totals.data(), d_totals, sizeof(long long) * (size_t)C, cudaMemcpyDeviceToHost, st) != cudaSuccess || cudaStreamSynchronize(st) != cudaSuccess) {
         return done(fail(TDM_ERR_CUDA, "tdm_process_long: %s", cudaGetErrorString(cudaGetLastError())));
     }
     if (cudaGetLastError() != cudaSuccess) { return done(fail(TDM_ERR_CUDA, "tdm_process_long: kernel launch failed")); }
-    info->n_dibits = total; info->n_segments = S; info->n_rerun = n_rerun; info->segment_samples = (int32_t)L; info->warmup = (int32_t)W;
-    if (total > dibits_cap) { return done(fail(TDM_ERR_ARG, "tdm_process_long: %lld dibits do not fit into dibits_cap %lld (output truncated)", total, (long long)dibits_cap)); }
+    long long sum = 0, worst = 0;
+    for (long long t : totals) { sum += t; if (t > worst) { worst = t; } }
+    info->n_dibits = sum; info->n_segments = S; info->n_rerun = n_rerun; info->segment_samples = (int32_t)L; info->warmup = (int32_t)W;
+    static_assert(sizeof(long long) == sizeof(int64_t), "counts are copied as they are");
     if (mem_kind == TDM_MEM_HOST) {
-        if (cudaMemcpy(dibits, d_tmp_out, (size_t)total, cudaMemcpyDeviceToHost) != cudaSuccess) { return done(fail(TDM_ERR_CUDA, "tdm_process_long: D2H copy failed")); }
+        std::memcpy(out_counts, totals.data(), sizeof(int64_t) * (size_t)C);
+    } else if (cudaMemcpyAsync(out_counts, d_totals, sizeof(int64_t) * (size_t)C, cudaMemcpyDeviceToDevice, st) != cudaSuccess) {
+        return done(fail(TDM_ERR_CUDA, "tdm_process_long: count copy failed"));
+    }
+    if (worst > out_stride) { return done(fail(TDM_ERR_ARG, "tdm_process_long: %lld dibits do not fit into out_stride %lld (rows truncated)", worst, (long long)out_stride)); }
+    if (mem_kind == TDM_MEM_HOST) {
+        if (cudaMemcpy2D(dibits, (size_t)out_stride, d_tmp_out, (size_t)out_stride, (size_t)worst, (size_t)C, cudaMemcpyDeviceToHost) != cudaSuccess) {
+            return done(fail(TDM_ERR_CUDA, "tdm_process_long: D2H copy failed"));
+        }
+    } else if (cudaStreamSynchronize(st) != cudaSuccess) {
+        return done(fail(TDM_ERR_CUDA, "tdm_process_long: %s", cudaGetErrorString(cudaGetLastError())));
     }
     return done(TDM_OK);
+}
+
+int tdm_process_long(tdm_handle* h, const float* iq, int64_t n_samples, int32_t warmup, uint8_t* dibits, int64_t dibits_cap,
+                     tdm_long_info* info, int32_t mem_kind) {
+    if (mem_kind == TDM_MEM_HOST) {
+        int64_t count = 0;
+        return tdm_process_long_batch(h, iq, n_samples, n_samples, 1, warmup, dibits, dibits_cap, &count, info, mem_kind);
+    }
+    if (!h) { return fail(TDM_ERR_ARG, "tdm_process_long: null handle"); }
+    DeviceGuard guard(h->device);
+    int64_t* d_count = nullptr;
+    TDM_CUDA(cudaMalloc(&d_count, sizeof(int64_t)));
+    const int rc = tdm_process_long_batch(h, iq, n_samples, n_samples, 1, warmup, dibits, dibits_cap, d_count, info, mem_kind);
+    cudaFree(d_count);
+    return rc;
 }
 
 int tdm_get_state(tdm_handle* h, tdm_channel_state* host_states, int32_t n_channels) {
@@ -496,14 +543,7 @@ int tdm_reset_all(tdm_handle* h) {
     if (!h) { return fail(TDM_ERR_ARG, "null handle"); }
     std::vector<tdm_channel_state> st((size_t)h->n_channels);
     for (auto& s : st) { init_state(h->design, s); }
-    if (h->d_long_state) {
-        DeviceGuard guard(h->device);
-        tdm_channel_state two[2];
-        init_state(h->design, two[0]);
-        two[1] = two[0];
-        TDM_CUDA(cudaMemcpyAsync(h->d_long_state, two, sizeof(two), cudaMemcpyHostToDevice, h->stream));
-        TDM_CUDA(cudaStreamSynchronize(h->stream));
-    }
+    h->long_channels = 0;                        // the next tdm_process_long[_batch] starts every channel from reset state
     return tdm_set_state(h, st.data(), h->n_channels);
 }
 

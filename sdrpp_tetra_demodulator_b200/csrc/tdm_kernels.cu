@@ -39,6 +39,14 @@ constexpr int kTapPad = TDM_TAP_PAD;
 constexpr int kITaps = TDM_INTERP_TAPS;    // 8
 constexpr int kIPhases = TDM_INTERP_PHASES;
 
+// First input sample of row `ch`.  Ordinarily rows are channels, in_stride apart.  For time-segmented captures
+// (tdm_process_long_batch) a row is segment (ch % rows_per_channel) of channel (ch / rows_per_channel): channels are
+// channel_stride apart, the segments of a channel in_stride apart (they overlap: in_stride < count).
+__device__ __forceinline__ const float2* row_input(const DemodParams& p, int ch) {
+    if (p.rows_per_channel <= 1) { return p.iq + (long long)ch * p.in_stride; }
+    return p.iq + (long long)(ch / p.rows_per_channel) * p.channel_stride + (long long)(ch % p.rows_per_channel) * p.in_stride;
+}
+
 template <int T>
 struct TpcLayout {
     static_assert(kHist % T == 0, "block length must divide the history length");
@@ -271,7 +279,7 @@ __global__ void __launch_bounds__(128) demod_tpc_kernel(const __grid_constant__ 
     }
     __syncthreads();   // bank_s visible
 
-    const float2* __restrict__ in = p.iq + (long long)ch * p.in_stride;
+    const float2* __restrict__ in = row_input(p, ch);
     const int count = p.count;
     const int nblk = (count + T - 1) / T;
 
@@ -506,7 +514,7 @@ __global__ void __launch_bounds__(160) demod_ws_kernel(const __grid_constant__ D
     // ---- role-private state
     float g = 0.f, fph = 0.f, ffr = 0.f;
     float2 cur[T], nxt[T];
-    const float2* __restrict__ in = p.iq + (long long)ch * p.in_stride;
+    const float2* __restrict__ in = row_input(p, ch);
     SymbolState st;
     float err_blocks[TDM_SYNC_BLOCKS];
     const int nsym0 = p.accumulate ? p.out_counts[ch] : 0;       // time-sliced calls append to the rows (tdm_api.cu)
@@ -794,7 +802,7 @@ __global__ void __launch_bounds__(WARPS * 32) demod_ws2_kernel(const __grid_cons
     // ---- role-private state
     float g = 0.f, fph = 0.f, ffr = 0.f, yr = 0.f, yi = 0.f;
     float2 cur[T], nxt[T];
-    const float2* __restrict__ in = p.iq + (long long)ch * p.in_stride;
+    const float2* __restrict__ in = row_input(p, ch);
     LoopConsts lc = {};
     float tria[T], trib[T], mida[2 * T - 1], midb[2 * T - 1];
     if (role == 0) {
@@ -1288,7 +1296,7 @@ __global__ void __launch_bounds__(Ws3Placement<PLACEMENT>::warps * 32) demod_ws3
         // The gain loop does not depend on anything downstream, so it runs as its own role: LOOP then carries
         // only the FLL recurrence (no sqrt chain, no global loads, ~25 % fewer instructions per sample).
         float g = sp->agc_gain;
-        const float2* __restrict__ in = p.iq + (long long)ch * p.in_stride;
+        const float2* __restrict__ in = row_input(p, ch);
         const LoopConsts lc = load_loop_consts(p);
         float2 cur[T], nxt[T];
 #pragma unroll

@@ -28,6 +28,8 @@ struct DemodParams {
     const float* bank;              // device [128][8] interpolator polyphase bank
     const float2* iq;               // [C][in_stride]
     long long in_stride;
+    long long channel_stride;       // only with rows_per_channel > 1 (see row_input() in tdm_kernels.cu)
+    int rows_per_channel;           // 0 / 1: every row is a channel
     int count;                      // samples per channel this launch
     int n_channels;
     float2* syms;                   // [C][out_stride] or nullptr
@@ -50,19 +52,21 @@ int launch_pack_dibits(const uint8_t* dibits, long long in_stride, const int* co
 int launch_synth(const tdm_synth_params& sp, int n_channels, long long n_samples, long long stride,
                  int first_channel, float2* iq, uint8_t* tx_dibits, long long tx_stride, cudaStream_t stream);
 
-// tdm_stitch.cu: joining the dibit streams of overlapping time segments (tdm_process_long)
-void launch_long_init_states(tdm_channel_state* states, const tdm_channel_state* carried, const tdm_channel_state* fresh, int n, cudaStream_t s);
-void launch_long_shift_states(tdm_channel_state* dst, const tdm_channel_state* src, int n, cudaStream_t s);
-void launch_stitch_find(const uint8_t* dib, long long stride, const int* counts, int n_rows, int K, int jlo, int jhi, int* join,
+// tdm_stitch.cu: joining the dibit streams of overlapping time segments (tdm_process_long[_batch]); S = segments per channel
+void launch_long_init_states(tdm_channel_state* states, const tdm_channel_state* carried, const tdm_channel_state* fresh, int n, int S, cudaStream_t s);
+void launch_long_shift_states(tdm_channel_state* dst, const tdm_channel_state* src, int n, int S, cudaStream_t s);
+void launch_long_last_states(tdm_channel_state* packed, tdm_channel_state* rows, int C, int S, int scatter, cudaStream_t s);
+void launch_stitch_find(const uint8_t* dib, long long stride, const int* counts, int n_rows, int S, int K, int jlo, int jhi, int* join,
                         const int* fixed, cudaStream_t s);
-void launch_stitch_plan(int* join, int* fixed, const int* counts, int n_rows, int* adopt, int* n_open, int* n_forced, int force_at,
+void launch_stitch_plan(int* join, int* fixed, const int* counts, int n_rows, int S, int* adopt, int* n_open, int* n_forced, int force_at,
                         int force_all, const tdm_channel_state* final_states, cudaStream_t s);
 void launch_stitch_adopt(uint8_t* dib, long long stride, const uint8_t* dib2, long long stride2, int* counts, const int* counts2, int* join,
                          int* fixed, const int* adopt, int* agree, int* mode, int* n_forced, int force_at, int K,
-                         tdm_channel_state* final_states, const tdm_channel_state* run_states, int n_rows, long long max_len, cudaStream_t s);
-void launch_stitch_scan(const int* counts, const int* join, int n_rows, long long* offs, cudaStream_t s);
-void launch_stitch_copy(const uint8_t* dib, long long stride, const int* counts, const int* join, const long long* offs, uint8_t* out,
-                        long long cap, int n_rows, long long max_len, cudaStream_t s);
-void launch_stitch_append(const uint8_t* src, const int* count, long long* total, uint8_t* out, long long cap, long long max_len, cudaStream_t s);
+                         tdm_channel_state* final_states, const tdm_channel_state* run_states, int n_rows, int S, long long max_len, cudaStream_t s);
+void launch_stitch_scan(const int* counts, const int* join, int n_rows, int S, long long* offs, long long* totals, cudaStream_t s);
+void launch_stitch_copy(const uint8_t* dib, long long stride, const int* counts, const int* join, const long long* offs, int S, uint8_t* out,
+                        long long out_stride, int n_rows, long long max_len, cudaStream_t s);
+void launch_stitch_append(const uint8_t* src, long long stride, const int* count, long long* totals, uint8_t* out, long long out_stride, int C,
+                          long long max_len, cudaStream_t s);
 
 }  // namespace tdm

@@ -1,16 +1,19 @@
-// tdm_stitch.cu -- kernels behind tdm_process_long (time-segment parallelism for ONE long
-// capture).  The demodulation chain is a recurrence in time, so a single channel cannot be split exactly; but
-// once its loops have converged, the decisions of a segment that started late from reset state are the same bits
-// the sequential chain produces.  tdm_process_long therefore runs S overlapping segments of one capture as S
-// "channels" of the batch kernel and joins their dibit streams here:
+// tdm_stitch.cu -- kernels behind tdm_process_long / tdm_process_long_batch (time-segment
+// parallelism for long captures of FEW channels).  The demodulation chain is a recurrence in time, so a channel
+// cannot be split exactly; but once its loops have converged, the decisions of a run that started late from reset
+// state are the same bits the sequential chain produces.  Each of C channels is therefore cut into S overlapping
+// segments, all C*S of them run as rows of the batch kernel (row r = c*S + s), and their dibit streams are joined here:
 //
-//   segment c covers samples [c L, (c+1) L + W): its first W samples are warm-up and are ALSO the last W samples
-//   of segment c-1.  The join is found by content: the last K dibits of segment c-1 must appear exactly once in
-//   segment c near symbol W/2; segment c contributes everything after that occurrence.  A segment whose warm-up
+//   segment s of a channel covers samples [s L, (s+1) L + W): its first W samples are warm-up and are ALSO the last W
+//   samples of segment s-1.  The join is found by content: the last K dibits of segment s-1 must appear exactly once
+//   in segment s near symbol W/2; segment s contributes everything after that occurrence.  A segment whose warm-up
 //   was not enough (no unique occurrence) is demodulated again, this time as the sequential continuation of its
-//   predecessor (from the predecessor's final loop state, samples [c L + W, (c+1) L + W)), which needs no join.
+//   predecessor (from the final loop state of the run that produced the predecessor's stream, samples
+//   [s L + W, (s+1) L + W)), which needs no join; its successor's join is then searched again against the new
+//   stream, because two converged runs may disagree by one symbol about what lies before a segment boundary.
 //
 // Bits only: the float loop states of later segments are not the sequential chain's (tdm_b200.h says so).
+// `S` below is segments per channel; rows with r % S == 0 are the first segment of a channel and never join.
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include "tdm_kernels.cuh"
@@ -18,30 +21,41 @@
 namespace tdm {
 namespace {
 
-// states[0] = the carried state of the logical channel, states[1..n) = a freshly initialised chain
-__global__ void long_init_states_kernel(tdm_channel_state* states, const tdm_channel_state* carried, const tdm_channel_state* fresh, int n) {
-    const int words = (int)(sizeof(tdm_channel_state) / 4);
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n * words; i += gridDim.x * blockDim.x) {
-        const int c = i / words, k = i % words;
-        reinterpret_cast<uint32_t*>(states + c)[k] = reinterpret_cast<const uint32_t*>(c == 0 ? carried : fresh)[k];
+constexpr int kStateWords = (int)(sizeof(tdm_channel_state) / 4);
+
+// states[r] = the carried state of its channel for first segments, a freshly initialised chain otherwise
+__global__ void long_init_states_kernel(tdm_channel_state* states, const tdm_channel_state* carried, const tdm_channel_state* fresh, int n, int S) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n * kStateWords; i += gridDim.x * blockDim.x) {
+        const int r = i / kStateWords, k = i % kStateWords;
+        const tdm_channel_state* src = (r % S == 0) ? carried + r / S : fresh;
+        reinterpret_cast<uint32_t*>(states + r)[k] = reinterpret_cast<const uint32_t*>(src)[k];
     }
 }
 
-// dst[c] = src[c - 1] for c >= 1: every segment becomes the continuation of its predecessor
-__global__ void long_shift_states_kernel(tdm_channel_state* dst, const tdm_channel_state* src, int n) {
-    const int words = (int)(sizeof(tdm_channel_state) / 4);
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n * words; i += gridDim.x * blockDim.x) {
-        const int c = i / words, k = i % words;
-        if (c >= 1) { reinterpret_cast<uint32_t*>(dst + c)[k] = reinterpret_cast<const uint32_t*>(src + c - 1)[k]; }
+// dst[r] = src[r - 1] within a channel: every segment becomes the continuation of its predecessor
+__global__ void long_shift_states_kernel(tdm_channel_state* dst, const tdm_channel_state* src, int n, int S) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n * kStateWords; i += gridDim.x * blockDim.x) {
+        const int r = i / kStateWords, k = i % kStateWords;
+        if (r % S != 0) { reinterpret_cast<uint32_t*>(dst + r)[k] = reinterpret_cast<const uint32_t*>(src + r - 1)[k]; }
     }
 }
 
-// one warp per join c = 1 .. n-1
-__global__ void stitch_find_kernel(const uint8_t* __restrict__ dib, long long stride, const int* __restrict__ counts, int n_rows,
+// dst[c] = src[c * S + S - 1] (gather the last segment's state of every channel) or the reverse (scatter)
+__global__ void long_last_states_kernel(tdm_channel_state* packed, tdm_channel_state* rows, int C, int S, int scatter) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < C * kStateWords; i += gridDim.x * blockDim.x) {
+        const int c = i / kStateWords, k = i % kStateWords;
+        uint32_t* a = reinterpret_cast<uint32_t*>(packed + c) + k;
+        uint32_t* b = reinterpret_cast<uint32_t*>(rows + (long long)c * S + S - 1) + k;
+        if (scatter) { *b = *a; } else { *a = *b; }
+    }
+}
+
+// one warp per row; rows that start a channel or are settled without agreement are skipped
+__global__ void stitch_find_kernel(const uint8_t* __restrict__ dib, long long stride, const int* __restrict__ counts, int n_rows, int S,
                                    int K, int jlo, int jhi, int* __restrict__ join, const int* __restrict__ fixed) {
     const int lane = threadIdx.x & 31;
-    const int c = 1 + blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (c >= n_rows) { return; }
+    const int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (c >= n_rows || c % S == 0) { return; }
     if (fixed[c]) { return; }                                   // a redone segment starts where its predecessor ended: join 0
     const int cp = counts[c - 1], cc = counts[c];
     int found = -1, total = 0;
@@ -64,28 +78,27 @@ __global__ void stitch_find_kernel(const uint8_t* __restrict__ dib, long long st
     if (lane == 0) { join[c] = (total == 1) ? found : -1; }
 }
 
-__device__ __forceinline__ bool seg_resolved(const int* join, const int* fixed, int c) { return c == 0 || fixed[c] || join[c] >= 0; }
+__device__ __forceinline__ bool seg_resolved(const int* join, const int* fixed, int r, int S) { return r % S == 0 || fixed[r] || join[r] >= 0; }
 
-// how many segments still have no place in the stream; which of them can be redone now (predecessor settled)
 // Which open segments can be redone now (predecessor settled), how many are left -- and which need no agreement at
 // all: if the run that produced the predecessor's stream is not locked at the boundary (DQPSKSymbolExtractor::sync of
 // its final state is down: a stretch without signal), there is nothing to agree on; such a segment is joined at the
 // nominal place, symbol force_at of its stream.  force_all: give up on every open segment the same way (pass limit).
-__global__ void stitch_plan_kernel(int* __restrict__ join, int* __restrict__ fixed, const int* __restrict__ counts, int n_rows,
+__global__ void stitch_plan_kernel(int* __restrict__ join, int* __restrict__ fixed, const int* __restrict__ counts, int n_rows, int S,
                                    int* __restrict__ adopt, int* __restrict__ n_open, int* __restrict__ n_forced, int force_at, int force_all,
                                    const tdm_channel_state* __restrict__ final_states) {
     if (blockIdx.x != 0 || threadIdx.x != 0) { return; }
     int open = 0, forced = 0;
-    for (int c = 1; c < n_rows; ++c) {
-        if (!seg_resolved(join, fixed, c) && (force_all || final_states[c - 1].sync == 0u)) {
-            join[c] = force_at < counts[c] ? force_at : counts[c];
-            fixed[c] = 2;                                           // settled without agreement: not searched again
+    for (int r = 0; r < n_rows; ++r) {
+        if (!seg_resolved(join, fixed, r, S) && (force_all || final_states[r - 1].sync == 0u)) {
+            join[r] = force_at < counts[r] ? force_at : counts[r];
+            fixed[r] = 2;                                           // settled without agreement: not searched again
             ++forced;
         }
     }
-    for (int c = 0; c < n_rows; ++c) {
-        const bool un = !seg_resolved(join, fixed, c);
-        adopt[c] = (un && seg_resolved(join, fixed, c - 1)) ? 1 : 0;
+    for (int r = 0; r < n_rows; ++r) {
+        const bool un = !seg_resolved(join, fixed, r, S);
+        adopt[r] = (un && seg_resolved(join, fixed, r - 1, S)) ? 1 : 0;     // un implies r % S != 0, so r - 1 is the same channel
         open += un ? 1 : 0;
     }
     *n_open = open;
@@ -123,16 +136,16 @@ __global__ void stitch_verify_kernel(const uint8_t* __restrict__ dib, long long 
 //           with each other and not with the predecessor's, so it is the predecessor's state that is off (observed: a
 //           run that started inside a stretch of noise can stay in a false lock for a million samples).
 __global__ void stitch_decide_kernel(int* __restrict__ join, int* __restrict__ fixed, const int* __restrict__ counts, const int* __restrict__ adopt,
-                                     const int* __restrict__ agree, int n_rows, int force_at, int* __restrict__ mode, int* __restrict__ n_forced) {
+                                     const int* __restrict__ agree, int n_rows, int S, int force_at, int* __restrict__ mode, int* __restrict__ n_forced) {
     if (blockIdx.x != 0 || threadIdx.x != 0) { return; }
-    for (int c = 0; c < n_rows; ++c) {
-        mode[c] = 0;
-        if (!adopt[c]) { continue; }
-        const bool successor_vouches = (c + 1 < n_rows) && !fixed[c + 1] && join[c + 1] >= 0;
-        mode[c] = (agree[c] || !successor_vouches) ? 1 : 2;
+    for (int r = 0; r < n_rows; ++r) {
+        mode[r] = 0;
+        if (!adopt[r]) { continue; }
+        const bool successor_vouches = (r + 1 < n_rows) && ((r + 1) % S != 0) && !fixed[r + 1] && join[r + 1] >= 0;
+        mode[r] = (agree[r] || !successor_vouches) ? 1 : 2;
     }
-    for (int c = 0; c < n_rows; ++c) {
-        if (mode[c] == 2) { join[c] = force_at < counts[c] ? force_at : counts[c]; fixed[c] = 2; *n_forced += 1; }
+    for (int r = 0; r < n_rows; ++r) {
+        if (mode[r] == 2) { join[r] = force_at < counts[r] ? force_at : counts[r]; fixed[r] = 2; *n_forced += 1; }
     }
 }
 
@@ -148,8 +161,7 @@ __global__ void stitch_adopt_kernel(uint8_t* __restrict__ dib, long long stride,
     uint8_t* __restrict__ dst = dib + (long long)c * stride;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < len; i += gridDim.x * blockDim.x) { dst[i] = src[i]; }
     if (blockIdx.x == 0) {
-        const int words = (int)(sizeof(tdm_channel_state) / 4);
-        for (int k = threadIdx.x; k < words; k += blockDim.x) {
+        for (int k = threadIdx.x; k < kStateWords; k += blockDim.x) {
             reinterpret_cast<uint32_t*>(final_states + c)[k] = reinterpret_cast<const uint32_t*>(run_states + c)[k];
         }
     }
@@ -157,85 +169,98 @@ __global__ void stitch_adopt_kernel(uint8_t* __restrict__ dib, long long stride,
     if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) { counts[c] = len; join[c] = 0; fixed[c] = 1; }
 }
 
-// lengths and exclusive offsets of every segment's contribution (n <= a few thousand: one thread)
-__global__ void stitch_scan_kernel(const int* __restrict__ counts, const int* __restrict__ join, int n_rows, long long* __restrict__ offs) {
-    if (blockIdx.x != 0 || threadIdx.x != 0) { return; }
+// lengths of every segment's contribution and their exclusive offsets inside the channel's output row; per-channel totals
+__global__ void stitch_scan_kernel(const int* __restrict__ counts, const int* __restrict__ join, int n_rows, int S, long long* __restrict__ offs,
+                                   long long* __restrict__ totals) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;                      // one thread per channel
+    if (c * S >= n_rows) { return; }
     long long acc = 0;
-    for (int c = 0; c < n_rows; ++c) {
-        offs[c] = acc;
-        acc += (c == 0) ? counts[0] : (join[c] >= 0 ? counts[c] - join[c] : 0);
+    for (int s = 0; s < S; ++s) {
+        const int r = c * S + s;
+        offs[r] = acc;
+        acc += (s == 0) ? counts[r] : (join[r] >= 0 ? counts[r] - join[r] : 0);
     }
-    offs[n_rows] = acc;
+    totals[c] = acc;
 }
 
-__global__ void stitch_copy_kernel(const uint8_t* __restrict__ dib, long long stride, const int* __restrict__ counts,
-                                   const int* __restrict__ join, const long long* __restrict__ offs, uint8_t* __restrict__ out, long long cap) {
-    const int c = blockIdx.y;
-    const int skip = (c == 0) ? 0 : join[c];
+__global__ void stitch_copy_kernel(const uint8_t* __restrict__ dib, long long stride, const int* __restrict__ counts, const int* __restrict__ join,
+                                   const long long* __restrict__ offs, int S, uint8_t* __restrict__ out, long long out_stride) {
+    const int r = blockIdx.y;
+    const int skip = (r % S == 0) ? 0 : join[r];
     if (skip < 0) { return; }
-    const uint8_t* __restrict__ src = dib + (long long)c * stride + skip;
-    const int len = counts[c] - skip;
-    const long long o = offs[c];
+    const uint8_t* __restrict__ src = dib + (long long)r * stride + skip;
+    const int len = counts[r] - skip;
+    const long long o = offs[r];
+    uint8_t* __restrict__ dst = out + (long long)(r / S) * out_stride;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < len; i += gridDim.x * blockDim.x) {
-        if (o + i < cap) { out[o + i] = src[i]; }
+        if (o + i < out_stride) { dst[o + i] = src[i]; }
     }
 }
 
-// append n dibits of row `src` at out[offs[slot] ..) and advance offs[slot] (tail of the capture)
-__global__ void stitch_append_kernel(const uint8_t* __restrict__ src, const int* __restrict__ count, long long* __restrict__ total,
-                                     uint8_t* __restrict__ out, long long cap) {
-    const long long o = *total;
-    const int len = *count;
+// append the tail run of every channel (row c of `src`, count[c] dibits) behind what the segments produced
+__global__ void stitch_append_kernel(const uint8_t* __restrict__ src, long long stride, const int* __restrict__ count, long long* __restrict__ totals,
+                                     uint8_t* __restrict__ out, long long out_stride) {
+    const int c = blockIdx.y;
+    const long long o = totals[c];
+    const int len = count[c];
+    const uint8_t* __restrict__ s = src + (long long)c * stride;
+    uint8_t* __restrict__ dst = out + (long long)c * out_stride;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < len; i += gridDim.x * blockDim.x) {
-        if (o + i < cap) { out[o + i] = src[i]; }
+        if (o + i < out_stride) { dst[o + i] = s[i]; }
     }
 }
-__global__ void stitch_bump_kernel(const int* __restrict__ count, long long* __restrict__ total) { *total += *count; }
+__global__ void stitch_bump_kernel(const int* __restrict__ count, long long* __restrict__ totals, int C) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c < C) { totals[c] += count[c]; }
+}
+
+unsigned blocks_for(long long n, int per, int cap) {
+    long long g = (n + per - 1) / per;
+    if (g > cap) { g = cap; }
+    if (g < 1) { g = 1; }
+    return (unsigned)g;
+}
 
 }  // namespace
 
-void launch_long_init_states(tdm_channel_state* states, const tdm_channel_state* carried, const tdm_channel_state* fresh, int n, cudaStream_t s) {
-    long_init_states_kernel<<<(n * 180 + 255) / 256, 256, 0, s>>>(states, carried, fresh, n);
+void launch_long_init_states(tdm_channel_state* states, const tdm_channel_state* carried, const tdm_channel_state* fresh, int n, int S, cudaStream_t s) {
+    long_init_states_kernel<<<blocks_for((long long)n * kStateWords, 256, 2048), 256, 0, s>>>(states, carried, fresh, n, S);
 }
-void launch_long_shift_states(tdm_channel_state* dst, const tdm_channel_state* src, int n, cudaStream_t s) {
-    long_shift_states_kernel<<<(n * 180 + 255) / 256, 256, 0, s>>>(dst, src, n);
+void launch_long_shift_states(tdm_channel_state* dst, const tdm_channel_state* src, int n, int S, cudaStream_t s) {
+    long_shift_states_kernel<<<blocks_for((long long)n * kStateWords, 256, 2048), 256, 0, s>>>(dst, src, n, S);
 }
-void launch_stitch_find(const uint8_t* dib, long long stride, const int* counts, int n_rows, int K, int jlo, int jhi, int* join,
+void launch_long_last_states(tdm_channel_state* packed, tdm_channel_state* rows, int C, int S, int scatter, cudaStream_t s) {
+    long_last_states_kernel<<<blocks_for((long long)C * kStateWords, 256, 2048), 256, 0, s>>>(packed, rows, C, S, scatter);
+}
+void launch_stitch_find(const uint8_t* dib, long long stride, const int* counts, int n_rows, int S, int K, int jlo, int jhi, int* join,
                         const int* fixed, cudaStream_t s) {
-    if (n_rows < 2) { return; }
-    stitch_find_kernel<<<(n_rows - 1 + 3) / 4, 128, 0, s>>>(dib, stride, counts, n_rows, K, jlo, jhi, join, fixed);
+    if (S < 2) { return; }
+    stitch_find_kernel<<<(n_rows + 3) / 4, 128, 0, s>>>(dib, stride, counts, n_rows, S, K, jlo, jhi, join, fixed);
 }
-void launch_stitch_plan(int* join, int* fixed, const int* counts, int n_rows, int* adopt, int* n_open, int* n_forced, int force_at,
+void launch_stitch_plan(int* join, int* fixed, const int* counts, int n_rows, int S, int* adopt, int* n_open, int* n_forced, int force_at,
                         int force_all, const tdm_channel_state* final_states, cudaStream_t s) {
-    stitch_plan_kernel<<<1, 32, 0, s>>>(join, fixed, counts, n_rows, adopt, n_open, n_forced, force_at, force_all, final_states);
+    stitch_plan_kernel<<<1, 32, 0, s>>>(join, fixed, counts, n_rows, S, adopt, n_open, n_forced, force_at, force_all, final_states);
 }
 void launch_stitch_adopt(uint8_t* dib, long long stride, const uint8_t* dib2, long long stride2, int* counts, const int* counts2, int* join,
                          int* fixed, const int* adopt, int* agree, int* mode, int* n_forced, int force_at, int K,
-                         tdm_channel_state* final_states, const tdm_channel_state* run_states, int n_rows, long long max_len, cudaStream_t s) {
-    long long gx = (max_len + 255) / 256;
-    if (gx > 256) { gx = 256; }
-    if (gx < 1) { gx = 1; }
+                         tdm_channel_state* final_states, const tdm_channel_state* run_states, int n_rows, int S, long long max_len, cudaStream_t s) {
     stitch_verify_kernel<<<(n_rows + 3) / 4, 128, 0, s>>>(dib, stride, dib2, stride2, counts, counts2, adopt, n_rows, K, agree);
-    stitch_decide_kernel<<<1, 32, 0, s>>>(join, fixed, counts, adopt, agree, n_rows, force_at, mode, n_forced);
-    stitch_adopt_kernel<<<dim3((unsigned)gx, (unsigned)n_rows), 256, 0, s>>>(dib, stride, dib2, stride2, counts, counts2, join, fixed, mode,
-                                                                           final_states, run_states);
+    stitch_decide_kernel<<<1, 32, 0, s>>>(join, fixed, counts, adopt, agree, n_rows, S, force_at, mode, n_forced);
+    stitch_adopt_kernel<<<dim3(blocks_for(max_len, 256, 256), (unsigned)n_rows), 256, 0, s>>>(dib, stride, dib2, stride2, counts, counts2, join, fixed,
+                                                                                              mode, final_states, run_states);
 }
-void launch_stitch_scan(const int* counts, const int* join, int n_rows, long long* offs, cudaStream_t s) {
-    stitch_scan_kernel<<<1, 32, 0, s>>>(counts, join, n_rows, offs);
+void launch_stitch_scan(const int* counts, const int* join, int n_rows, int S, long long* offs, long long* totals, cudaStream_t s) {
+    const int C = n_rows / S;
+    stitch_scan_kernel<<<(C + 127) / 128, 128, 0, s>>>(counts, join, n_rows, S, offs, totals);
 }
-void launch_stitch_copy(const uint8_t* dib, long long stride, const int* counts, const int* join, const long long* offs, uint8_t* out,
-                        long long cap, int n_rows, long long max_len, cudaStream_t s) {
-    long long gx = (max_len + 255) / 256;
-    if (gx > 512) { gx = 512; }
-    if (gx < 1) { gx = 1; }
-    stitch_copy_kernel<<<dim3((unsigned)gx, (unsigned)n_rows), 256, 0, s>>>(dib, stride, counts, join, offs, out, cap);
+void launch_stitch_copy(const uint8_t* dib, long long stride, const int* counts, const int* join, const long long* offs, int S, uint8_t* out,
+                        long long out_stride, int n_rows, long long max_len, cudaStream_t s) {
+    stitch_copy_kernel<<<dim3(blocks_for(max_len, 256, 512), (unsigned)n_rows), 256, 0, s>>>(dib, stride, counts, join, offs, S, out, out_stride);
 }
-void launch_stitch_append(const uint8_t* src, const int* count, long long* total, uint8_t* out, long long cap, long long max_len, cudaStream_t s) {
-    long long gx = (max_len + 255) / 256;
-    if (gx > 512) { gx = 512; }
-    if (gx < 1) { gx = 1; }
-    stitch_append_kernel<<<(unsigned)gx, 256, 0, s>>>(src, count, total, out, cap);
-    stitch_bump_kernel<<<1, 1, 0, s>>>(count, total);
+void launch_stitch_append(const uint8_t* src, long long stride, const int* count, long long* totals, uint8_t* out, long long out_stride, int C,
+                          long long max_len, cudaStream_t s) {
+    stitch_append_kernel<<<dim3(blocks_for(max_len, 256, 64), (unsigned)C), 256, 0, s>>>(src, stride, count, totals, out, out_stride);
+    stitch_bump_kernel<<<(C + 127) / 128, 128, 0, s>>>(count, totals, C);
 }
 
 }  // namespace tdm

@@ -207,6 +207,33 @@ class Demodulator:
         d = {f: int(getattr(info, f)) for f, _ in capi.TdmLongInfo._fields_}
         return dib[:d["n_dibits"]], d
 
+    def process_long_batch(self, iq, warmup: int = 65536, out=None):
+        """C long captures at once ([C][N][2] float32, CUDA tensor or numpy array), every channel cut into
+        n_channels // C overlapping time segments (tdm_process_long_batch; decoded dibits only).
+        Returns (dibits [C][N // 2 + 64] uint8, counts [C] int64, info dict) -- same kind of arrays as `iq`."""
+        info = capi.TdmLongInfo()
+        Cn, n = int(iq.shape[0]), int(iq.shape[1])
+        stride = n // 2 + 64
+        if isinstance(iq, np.ndarray):
+            iq = np.ascontiguousarray(iq, dtype=np.float32)
+            dib = np.zeros((Cn, stride), np.uint8) if out is None else out
+            cnt = np.zeros(Cn, np.int64)
+            capi.check(self._lib.tdm_process_long_batch(self._h, iq.ctypes.data_as(C.c_void_p), n, n, Cn, warmup, dib.ctypes.data_as(C.c_void_p),
+                                                        dib.shape[1], cnt.ctypes.data_as(C.c_void_p), C.byref(info), capi.TDM_MEM_HOST),
+                       "tdm_process_long_batch")
+        else:
+            torch = _torch()
+            if not (iq.is_cuda and iq.dtype == torch.float32 and iq.dim() == 3 and iq.shape[2] == 2 and iq.stride(2) == 1 and iq.stride(1) == 2):
+                raise ValueError("iq must be a CUDA float32 tensor [C][N][2] with contiguous rows")
+            self.set_stream(torch.cuda.current_stream(iq.device).cuda_stream)
+            dib = torch.empty((Cn, stride), dtype=torch.uint8, device=iq.device) if out is None else out
+            cnt = torch.empty(Cn, dtype=torch.int64, device=iq.device)
+            capi.check(self._lib.tdm_process_long_batch(self._h, C.c_void_p(iq.data_ptr()), iq.stride(0) // 2, n, Cn, warmup,
+                                                        C.c_void_p(dib.data_ptr()), dib.shape[1], C.c_void_p(cnt.data_ptr()), C.byref(info),
+                                                        capi.TDM_MEM_DEVICE), "tdm_process_long_batch")
+        d = {f: int(getattr(info, f)) for f, _ in capi.TdmLongInfo._fields_}
+        return dib, cnt, d
+
     def pack_dibits(self, dibits, counts):
         """4 dibits per byte (first symbol in bits 7..6): the form shipped over NVLink by the multi-GPU gather."""
         torch = _torch()

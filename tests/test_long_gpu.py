@@ -133,6 +133,41 @@ def test_stretch_without_signal(O, pkg, torch_cuda):
     assert best == 0, best
 
 
+def test_batch_of_long_captures(O, pkg, torch_cuda):
+    """tdm_process_long_batch (BASELINE.json configs[2] in small): every channel cut into rows // C segments; each
+    channel's stream equals its own sequential chain after lock; a second call continues every channel; host buffers
+    give the same as device buffers"""
+    torch = torch_cuda
+    C_, N = 3, 900_000
+    iq = O.generate(C_, N, first_channel=4)
+    seqs = [_sequential(O, iq[c]) for c in range(C_)]
+    with pkg.Demodulator(24, 1024) as dm, pkg.Demodulator(24, 1024) as dm_host:
+        dib, cnt, info = dm.process_long_batch(torch.from_numpy(iq).cuda(), warmup=20_000)
+        torch.cuda.synchronize()
+        assert info["n_segments"] == 8 and info["warmup"] == 20_000, info
+        dib, cnt = dib.cpu().numpy(), cnt.cpu().numpy()
+        hd, hc, hinfo = dm_host.process_long_batch(iq, warmup=20_000)
+        assert np.array_equal(hc, cnt) and all(np.array_equal(hd[c, :cnt[c]], dib[c, :cnt[c]]) for c in range(C_))
+        assert info["n_dibits"] == int(cnt.sum())
+        for c in range(C_):
+            got, seq = dib[c, :cnt[c]], seqs[c]
+            assert abs(len(got) - len(seq)) <= 1, (c, len(got), len(seq), info)
+            n = min(len(got), len(seq))
+            assert np.array_equal(got[100_000:n], seq[100_000:n]), (c, info)
+            assert np.array_equal(got[:info["segment_samples"] // 2], seq[:info["segment_samples"] // 2])      # first segments ARE sequential
+        # second call: every channel continues its own stream
+        more = O.generate(C_, N, first_channel=4, n0=N)               # the generator is a function of the sample index
+        full = [_sequential(O, np.concatenate([iq[c], more[c]])) for c in range(C_)]
+        dib2, cnt2, info2 = dm.process_long_batch(torch.from_numpy(np.ascontiguousarray(more)).cuda(), warmup=20_000)
+        torch.cuda.synchronize()
+        dib2, cnt2 = dib2.cpu().numpy(), cnt2.cpu().numpy()
+        for c in range(C_):
+            got = np.concatenate([dib[c, :cnt[c]], dib2[c, :cnt2[c]]])
+            assert abs(len(got) - len(full[c])) <= 1
+            n = min(len(got), len(full[c]))
+            assert np.array_equal(got[100_000:n], full[c][100_000:n]), c
+
+
 def test_argument_checks(pkg, torch_cuda):
     torch = torch_cuda
     with pkg.Demodulator(4, 1024) as dm:
