@@ -193,12 +193,12 @@ int tdm_process(tdm_handle* h, const float* iq, int64_t in_stride, int32_t count
 typedef struct tdm_long_info {
     int64_t n_dibits;          /* dibits written                                                  */
     int32_t n_segments;        /* segments actually used (fewer for short captures)              */
-    int32_t n_rerun;           /* segments that had to be redone sequentially (join not found)    */
+    int32_t n_rerun;           /* segments whose join was not found at the first attempt          */
     int32_t segment_samples;   /* L                                                               */
     int32_t warmup;            /* W actually used (0 when a single segment was enough)            */
     int32_t n_forced;          /* segments joined at the nominal place: predecessor not locked there (no signal),
                                   or its continuation contradicted by two independent later runs             */
-    int32_t reserved;
+    int32_t n_extended;        /* of n_rerun, segments that joined after their predecessor ran on a little (no redo) */
 } tdm_long_info;
 int tdm_process_long(tdm_handle* h, const float* iq, int64_t n_samples, int32_t warmup, uint8_t* dibits, int64_t dibits_cap,
                      tdm_long_info* info, int32_t mem_kind);

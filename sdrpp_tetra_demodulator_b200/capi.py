@@ -88,7 +88,7 @@ class TdmSynthParams(C.Structure):
 
 class TdmLongInfo(C.Structure):
     _fields_ = [("n_dibits", C.c_int64), ("n_segments", C.c_int32), ("n_rerun", C.c_int32),
-                ("segment_samples", C.c_int32), ("warmup", C.c_int32), ("n_forced", C.c_int32), ("reserved", C.c_int32)]
+                ("segment_samples", C.c_int32), ("warmup", C.c_int32), ("n_forced", C.c_int32), ("n_extended", C.c_int32)]
 
 
 class TdmMetrics(C.Structure):

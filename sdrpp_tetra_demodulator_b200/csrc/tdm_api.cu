@@ -346,9 +346,11 @@ int tdm_process_long_batch(tdm_handle* h, const float* iq, int64_t in_stride, in
     // symbols before the hand-over sends those segments to the sequential redo instead.
     int K = warmup / 8;
     K = K < 128 ? 128 : (K > 4096 ? 4096 : K);
-    // S segments per channel: rows of L + W samples, segment s starts at sample s L; a segment must dwarf its warm-up
+    // S segments per channel: rows of L + W samples, segment s starts at sample s L.  A launch lasts as long as its
+    // longest row ((L + W) samples at one recurrence's pace), so more, shorter segments pay as long as L stays well
+    // above W: below 2 W the warm-up is more than a third of the work.
     int S = h->n_channels / C;
-    const long long min_seg = 4LL * warmup;
+    const long long min_seg = 2LL * warmup;
     if ((n_samples - warmup) / S < min_seg) { S = (int)((n_samples - warmup) / min_seg); }
     if (S < 1) { S = 1; }
     const long long L = (S > 1) ? (((n_samples - warmup) / S) & ~7LL) : n_samples;
@@ -356,7 +358,11 @@ int tdm_process_long_batch(tdm_handle* h, const float* iq, int64_t in_stride, in
     if (L + W > 0x7fffffffLL) { return fail(TDM_ERR_ARG, "tdm_process_long: segments of %lld samples exceed the 32-bit count of a launch; use more rows", L + W); }
     const long long covered = (S > 1) ? S * L + W : n_samples;
     const long long tail = n_samples - covered;                 // < 9 S samples per channel, demodulated sequentially at the end
-    const long long need = max_symbols_for(h->design, L + W);
+    // extension rounds: predecessors of segments that have not converged in time run on a little past their end and the
+    // join is tried again further in (costs kExtSamples at one recurrence's pace instead of a whole segment's redo)
+    constexpr int kExtRounds = 2;
+    const long long X = (S > 1) ? ((L / 4 < 32768 ? L / 4 : 32768) & ~7LL) : 0;
+    const long long need = max_symbols_for(h->design, L + W + kExtRounds * X);
     const int R = C * S;
 
     // scratch (sized for the handle's rows once)
@@ -372,7 +378,7 @@ int tdm_process_long_batch(tdm_handle* h, const float* iq, int64_t in_stride, in
     tdm_channel_state* d_carried = h->d_long_state;
     tdm_channel_state* d_fresh = h->d_long_state + C;
     if (!h->d_states2) { TDM_CUDA(cudaMalloc(&h->d_states2, sizeof(tdm_channel_state) * HR)); }
-    if (!h->d_seg_ints) { TDM_CUDA(cudaMalloc(&h->d_seg_ints, sizeof(int) * (8 * HR + 4))); }
+    if (!h->d_seg_ints) { TDM_CUDA(cudaMalloc(&h->d_seg_ints, sizeof(int) * (10 * HR + 4))); }
     if (!h->d_offs) { TDM_CUDA(cudaMalloc(&h->d_offs, sizeof(long long) * (2 * HR + 2))); }
     if (h->seg_stride < need) {
         cudaFree(h->d_seg_dibits); h->d_seg_dibits = nullptr; h->seg_stride = 0;
@@ -386,7 +392,9 @@ int tdm_process_long_batch(tdm_handle* h, const float* iq, int64_t in_stride, in
     int* d_adopt = d_fixed + HR;
     int* d_agree = d_adopt + HR;
     int* d_mode = d_agree + HR;
-    int* d_tailcount = d_mode + HR;                              // [C]
+    int* d_cut = d_mode + HR;
+    int* d_tails = d_cut + HR;
+    int* d_tailcount = d_tails + HR;                             // [C]
     int* d_nopen = d_tailcount + HR;
     int* d_nforced = d_nopen + 1;
     long long* d_offs = h->d_offs;
@@ -429,12 +437,15 @@ int tdm_process_long_batch(tdm_handle* h, const float* iq, int64_t in_stride, in
     int n_rerun = 0;
     if (S > 1) {
         if (cudaMemsetAsync(d_fixed, 0, sizeof(int) * (size_t)R, st) != cudaSuccess || cudaMemsetAsync(d_nforced, 0, sizeof(int), st) != cudaSuccess ||
+            cudaMemsetAsync(d_cut, 0, sizeof(int) * (size_t)R, st) != cudaSuccess ||
             cudaMemcpyAsync(h->d_states2, h->d_states, sizeof(tdm_channel_state) * (size_t)R, cudaMemcpyDeviceToDevice, st) != cudaSuccess) {
             return done(fail(TDM_ERR_CUDA, "tdm_process_long: %s", cudaGetErrorString(cudaGetLastError())));
         }
         tdm_channel_state* d_final = h->d_states2;                     // final loop state of the run whose stream each segment uses
+        long long ext_total = 0;
+        int ext_rounds = 0;
         for (int pass = 0;; ++pass) {
-            tdm::launch_stitch_find(h->d_seg_dibits, h->seg_stride, d_counts, R, S, K, mid - 2048, mid + 256, d_join, d_fixed, st);
+            tdm::launch_stitch_find(h->d_seg_dibits, h->seg_stride, d_counts, d_counts, R, S, K, mid - 2048, mid + 256, d_join, d_fixed, d_cut, 0, st);
             // A segment whose predecessor is not locked at the boundary (no signal there) is joined at the nominal place
             // right away; the pass limit only guards against pathological inputs.
             const bool give_up = pass >= 64;
@@ -445,6 +456,36 @@ int tdm_process_long_batch(tdm_handle* h, const float* iq, int64_t in_stride, in
             }
             if (n_open == 0) { break; }
             if (pass == 0) { n_rerun = n_open; }
+            if (pass == 0 && X >= 4096 && R > 1) {
+                // ---- extension rounds (only straight after pass 1: the rows' states are still their pass-1 finals).  Every
+                // row but the very last runs on for X samples, appending to its own stream; an open segment then looks for
+                // the extended predecessor's tail around symbol (W + ext) / 2 of its own stream.  The last row of the
+                // buffer is left out (there is nothing behind it to read); other channel-final rows read into the next
+                // channel, which is harmless: nobody joins them, and the carried states come from d_final.
+                if (cudaMemcpyAsync(d_tails, d_counts, sizeof(int) * (size_t)R, cudaMemcpyDeviceToDevice, st) != cudaSuccess) {
+                    return done(fail(TDM_ERR_CUDA, "tdm_process_long: copy failed"));
+                }
+                while (n_open > 0 && ext_rounds < kExtRounds) {
+                    tdm::DemodParams e = p;
+                    e.n_channels = R - 1;
+                    e.iq = d_iq + (L + W) + ext_total; e.count = (int)X; e.accumulate = 1; e.out_counts = d_tails;
+                    n = tdm::launch_demod(e, h->variant, st);
+                    if (n < 0) { return done(fail(TDM_ERR_CUDA, "demod kernel launch failed: %s", cudaGetErrorString(cudaGetLastError()))); }
+                    h->launches += n;
+                    ext_total += X; ++ext_rounds;
+                    const int mid_e = (int)((W + ext_total) / 2);
+                    int Ke = (int)((W + ext_total) / 8);                // the same rule as K, for the longer run-in
+                    Ke = Ke < 128 ? 128 : (Ke > 4096 ? 4096 : Ke);
+                    tdm::launch_stitch_find(h->d_seg_dibits, h->seg_stride, d_counts, d_tails, R, S, Ke, mid_e - 2048, mid_e + 256, d_join, d_fixed,
+                                            d_cut, 1, st);
+                    tdm::launch_stitch_plan(d_join, d_fixed, d_counts, R, S, d_adopt, d_nopen, d_nforced, mid, 0, d_final, st);
+                    if (cudaMemcpyAsync(&n_open, d_nopen, sizeof(int), cudaMemcpyDeviceToHost, st) != cudaSuccess || cudaStreamSynchronize(st) != cudaSuccess) {
+                        return done(fail(TDM_ERR_CUDA, "tdm_process_long: %s", cudaGetErrorString(cudaGetLastError())));
+                    }
+                }
+                info->n_extended = n_rerun - n_open;
+                if (n_open == 0) { break; }
+            }
             const long long need2 = max_symbols_for(h->design, L);
             if (h->seg_stride2 < need2) {
                 cudaFree(h->d_seg_dibits2); h->d_seg_dibits2 = nullptr; h->seg_stride2 = 0;
@@ -469,8 +510,9 @@ int tdm_process_long_batch(tdm_handle* h, const float* iq, int64_t in_stride, in
     } else {
         tdm::launch_long_last_states(d_carried, h->d_states, C, 1, 0, st);
     }
-    tdm::launch_stitch_scan(d_counts, d_join, R, S, d_offs, d_totals, st);
-    tdm::launch_stitch_copy(h->d_seg_dibits, h->seg_stride, d_counts, d_join, d_offs, S, d_out, out_stride, R, need, st);
+    if (S == 1) { TDM_CUDA(cudaMemsetAsync(d_cut, 0, sizeof(int) * (size_t)R, st)); }
+    tdm::launch_stitch_scan(d_counts, d_cut, d_join, R, S, d_offs, d_totals, st);
+    tdm::launch_stitch_copy(h->d_seg_dibits, h->seg_stride, d_counts, d_cut, d_join, d_offs, S, d_out, out_stride, R, need, st);
     // ---- the few samples the equal segments did not cover: sequentially, every channel from its last state (now in d_carried)
     if (tail > 0) {
         tdm::DemodParams q = p;

@@ -56,16 +56,16 @@ int launch_synth(const tdm_synth_params& sp, int n_channels, long long n_samples
 void launch_long_init_states(tdm_channel_state* states, const tdm_channel_state* carried, const tdm_channel_state* fresh, int n, int S, cudaStream_t s);
 void launch_long_shift_states(tdm_channel_state* dst, const tdm_channel_state* src, int n, int S, cudaStream_t s);
 void launch_long_last_states(tdm_channel_state* packed, tdm_channel_state* rows, int C, int S, int scatter, cudaStream_t s);
-void launch_stitch_find(const uint8_t* dib, long long stride, const int* counts, int n_rows, int S, int K, int jlo, int jhi, int* join,
-                        const int* fixed, cudaStream_t s);
+void launch_stitch_find(const uint8_t* dib, long long stride, const int* counts, const int* tails, int n_rows, int S, int K, int jlo, int jhi,
+                        int* join, int* fixed, int* cut, int late, cudaStream_t s);
 void launch_stitch_plan(int* join, int* fixed, const int* counts, int n_rows, int S, int* adopt, int* n_open, int* n_forced, int force_at,
                         int force_all, const tdm_channel_state* final_states, cudaStream_t s);
 void launch_stitch_adopt(uint8_t* dib, long long stride, const uint8_t* dib2, long long stride2, int* counts, const int* counts2, int* join,
                          int* fixed, const int* adopt, int* agree, int* mode, int* n_forced, int force_at, int K,
                          tdm_channel_state* final_states, const tdm_channel_state* run_states, int n_rows, int S, long long max_len, cudaStream_t s);
-void launch_stitch_scan(const int* counts, const int* join, int n_rows, int S, long long* offs, long long* totals, cudaStream_t s);
-void launch_stitch_copy(const uint8_t* dib, long long stride, const int* counts, const int* join, const long long* offs, int S, uint8_t* out,
-                        long long out_stride, int n_rows, long long max_len, cudaStream_t s);
+void launch_stitch_scan(const int* counts, const int* cut, const int* join, int n_rows, int S, long long* offs, long long* totals, cudaStream_t s);
+void launch_stitch_copy(const uint8_t* dib, long long stride, const int* counts, const int* cut, const int* join, const long long* offs, int S,
+                        uint8_t* out, long long out_stride, int n_rows, long long max_len, cudaStream_t s);
 void launch_stitch_append(const uint8_t* src, long long stride, const int* count, long long* totals, uint8_t* out, long long out_stride, int C,
                           long long max_len, cudaStream_t s);
 

@@ -51,13 +51,18 @@ __global__ void long_last_states_kernel(tdm_channel_state* packed, tdm_channel_s
 }
 
 // one warp per row; rows that start a channel or are settled without agreement are skipped
-__global__ void stitch_find_kernel(const uint8_t* __restrict__ dib, long long stride, const int* __restrict__ counts, int n_rows, int S,
-                                   int K, int jlo, int jhi, int* __restrict__ join, const int* __restrict__ fixed) {
+// `tails`: how long every row's stream is as a PREDECESSOR (its own length, or more once it has been extended past its
+// end); `late` != 0: this is a retry against extended predecessors -- a success also records where the predecessor's
+// contribution ends (cut) and settles the row for good (fixed = 3).
+__global__ void stitch_find_kernel(const uint8_t* __restrict__ dib, long long stride, const int* __restrict__ counts, const int* __restrict__ tails,
+                                   int n_rows, int S, int K, int jlo, int jhi, int* __restrict__ join, int* __restrict__ fixed,
+                                   int* __restrict__ cut, int late) {
     const int lane = threadIdx.x & 31;
     const int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (c >= n_rows || c % S == 0) { return; }
-    if (fixed[c]) { return; }                                   // a redone segment starts where its predecessor ended: join 0
-    const int cp = counts[c - 1], cc = counts[c];
+    if (fixed[c]) { return; }                                   // settled: redone (join 0), joined late, or joined without agreement
+    if (late && join[c] >= 0) { return; }
+    const int cp = tails[c - 1], cc = counts[c];
     int found = -1, total = 0;
     if (cp >= K) {
         const uint8_t* __restrict__ tail = dib + (long long)(c - 1) * stride + (cp - K);
@@ -75,7 +80,11 @@ __global__ void stitch_find_kernel(const uint8_t* __restrict__ dib, long long st
             }
         }
     }
-    if (lane == 0) { join[c] = (total == 1) ? found : -1; }
+    if (lane == 0) {
+        const int j = (total == 1) ? found : -1;
+        join[c] = j;
+        if (late && j >= 0) { fixed[c] = 3; cut[c - 1] = cp; }
+    }
 }
 
 __device__ __forceinline__ bool seg_resolved(const int* join, const int* fixed, int r, int S) { return r % S == 0 || fixed[r] || join[r] >= 0; }
@@ -170,26 +179,28 @@ __global__ void stitch_adopt_kernel(uint8_t* __restrict__ dib, long long stride,
 }
 
 // lengths of every segment's contribution and their exclusive offsets inside the channel's output row; per-channel totals
-__global__ void stitch_scan_kernel(const int* __restrict__ counts, const int* __restrict__ join, int n_rows, int S, long long* __restrict__ offs,
-                                   long long* __restrict__ totals) {
+// (cut[r] > 0: row r was extended past its end and its late-joining successor takes over only at symbol cut[r])
+__global__ void stitch_scan_kernel(const int* __restrict__ counts, const int* __restrict__ cut, const int* __restrict__ join, int n_rows, int S,
+                                   long long* __restrict__ offs, long long* __restrict__ totals) {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;                      // one thread per channel
     if (c * S >= n_rows) { return; }
     long long acc = 0;
     for (int s = 0; s < S; ++s) {
         const int r = c * S + s;
         offs[r] = acc;
-        acc += (s == 0) ? counts[r] : (join[r] >= 0 ? counts[r] - join[r] : 0);
+        const int end = cut[r] > 0 ? cut[r] : counts[r];
+        acc += (s == 0) ? end : (join[r] >= 0 ? end - join[r] : 0);
     }
     totals[c] = acc;
 }
 
-__global__ void stitch_copy_kernel(const uint8_t* __restrict__ dib, long long stride, const int* __restrict__ counts, const int* __restrict__ join,
-                                   const long long* __restrict__ offs, int S, uint8_t* __restrict__ out, long long out_stride) {
+__global__ void stitch_copy_kernel(const uint8_t* __restrict__ dib, long long stride, const int* __restrict__ counts, const int* __restrict__ cut,
+                                   const int* __restrict__ join, const long long* __restrict__ offs, int S, uint8_t* __restrict__ out, long long out_stride) {
     const int r = blockIdx.y;
     const int skip = (r % S == 0) ? 0 : join[r];
     if (skip < 0) { return; }
     const uint8_t* __restrict__ src = dib + (long long)r * stride + skip;
-    const int len = counts[r] - skip;
+    const int len = (cut[r] > 0 ? cut[r] : counts[r]) - skip;
     const long long o = offs[r];
     uint8_t* __restrict__ dst = out + (long long)(r / S) * out_stride;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < len; i += gridDim.x * blockDim.x) {
@@ -232,10 +243,10 @@ void launch_long_shift_states(tdm_channel_state* dst, const tdm_channel_state* s
 void launch_long_last_states(tdm_channel_state* packed, tdm_channel_state* rows, int C, int S, int scatter, cudaStream_t s) {
     long_last_states_kernel<<<blocks_for((long long)C * kStateWords, 256, 2048), 256, 0, s>>>(packed, rows, C, S, scatter);
 }
-void launch_stitch_find(const uint8_t* dib, long long stride, const int* counts, int n_rows, int S, int K, int jlo, int jhi, int* join,
-                        const int* fixed, cudaStream_t s) {
+void launch_stitch_find(const uint8_t* dib, long long stride, const int* counts, const int* tails, int n_rows, int S, int K, int jlo, int jhi,
+                        int* join, int* fixed, int* cut, int late, cudaStream_t s) {
     if (S < 2) { return; }
-    stitch_find_kernel<<<(n_rows + 3) / 4, 128, 0, s>>>(dib, stride, counts, n_rows, S, K, jlo, jhi, join, fixed);
+    stitch_find_kernel<<<(n_rows + 3) / 4, 128, 0, s>>>(dib, stride, counts, tails, n_rows, S, K, jlo, jhi, join, fixed, cut, late);
 }
 void launch_stitch_plan(int* join, int* fixed, const int* counts, int n_rows, int S, int* adopt, int* n_open, int* n_forced, int force_at,
                         int force_all, const tdm_channel_state* final_states, cudaStream_t s) {
@@ -249,13 +260,13 @@ void launch_stitch_adopt(uint8_t* dib, long long stride, const uint8_t* dib2, lo
     stitch_adopt_kernel<<<dim3(blocks_for(max_len, 256, 256), (unsigned)n_rows), 256, 0, s>>>(dib, stride, dib2, stride2, counts, counts2, join, fixed,
                                                                                               mode, final_states, run_states);
 }
-void launch_stitch_scan(const int* counts, const int* join, int n_rows, int S, long long* offs, long long* totals, cudaStream_t s) {
+void launch_stitch_scan(const int* counts, const int* cut, const int* join, int n_rows, int S, long long* offs, long long* totals, cudaStream_t s) {
     const int C = n_rows / S;
-    stitch_scan_kernel<<<(C + 127) / 128, 128, 0, s>>>(counts, join, n_rows, S, offs, totals);
+    stitch_scan_kernel<<<(C + 127) / 128, 128, 0, s>>>(counts, cut, join, n_rows, S, offs, totals);
 }
-void launch_stitch_copy(const uint8_t* dib, long long stride, const int* counts, const int* join, const long long* offs, int S, uint8_t* out,
-                        long long out_stride, int n_rows, long long max_len, cudaStream_t s) {
-    stitch_copy_kernel<<<dim3(blocks_for(max_len, 256, 512), (unsigned)n_rows), 256, 0, s>>>(dib, stride, counts, join, offs, S, out, out_stride);
+void launch_stitch_copy(const uint8_t* dib, long long stride, const int* counts, const int* cut, const int* join, const long long* offs, int S,
+                        uint8_t* out, long long out_stride, int n_rows, long long max_len, cudaStream_t s) {
+    stitch_copy_kernel<<<dim3(blocks_for(max_len, 256, 512), (unsigned)n_rows), 256, 0, s>>>(dib, stride, counts, cut, join, offs, S, out, out_stride);
 }
 void launch_stitch_append(const uint8_t* src, long long stride, const int* count, long long* totals, uint8_t* out, long long out_stride, int C,
                           long long max_len, cudaStream_t s) {

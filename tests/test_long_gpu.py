@@ -41,7 +41,7 @@ def test_segmented_equals_sequential_after_lock(O, pkg, torch_cuda, snr_db, chan
         got, info = dm.process_long(torch.from_numpy(iq).cuda(), warmup=32768)
         torch.cuda.synchronize()
         got = got.cpu().numpy()
-    assert info["n_segments"] == 8 and info["warmup"] == 32768, info      # (N - W) / 16 < 4 W: fewer, longer segments
+    assert info["n_segments"] == 16 and info["warmup"] == 32768, info
     assert abs(len(got) - len(seq)) <= 1, (len(got), len(seq), info)
     n = min(len(got), len(seq))
     assert np.array_equal(got[lock:n], seq[lock:n]), (info, np.flatnonzero(got[lock:n] != seq[lock:n])[:10] + lock)
