@@ -1193,7 +1193,9 @@ __device__ __forceinline__ void slicer_symbols(const DemodParams& p, const float
 #pragma unroll
     for (int k = 0; k < NS; ++k) {
         const bool v = k < n;
-        const float2 u = us[(base + k) & (RING - 1)][lane];
+        // (predicated: entries past n may be the ones COSTAS is writing during this very tick -- the value would be
+        // discarded anyway, but an unguarded read is a shared-memory race as far as compute-sanitizer can tell)
+        const float2 u = v ? us[(base + k) & (RING - 1)][lane] : make_float2(0.f, 0.f);
         const bool a = u.y < 0.f, b = u.x < 0.f;
         const float dist = quadrant_phase_error(u.x, u.y);     // |ideal.phase() - sym.phase()|, dqpsk_sym_extr.cpp:8-11
         const float ep = add_rn(sl.err_partial, dist);
@@ -1246,7 +1248,9 @@ struct Ws3Smem {
 // All warps of the CTA meet here once per tick.  Spelled as the PTX barrier because every role runs its
 // OWN tick loop (no per-tick role dispatch, no registers of other roles live): the warps arrive at barrier 0
 // from different program counters, whole warps at a time, the same number of times (ws3_ticks()).
-__device__ __forceinline__ void ws3_tick_barrier() { asm volatile("bar.sync 0;" ::: "memory"); }
+// The thread count is spelled out (every ws3 placement has 12 warps): the barrier is reached from different program
+// counters, which is exactly what the counted form is for (and what compute-sanitizer's synccheck accepts).
+__device__ __forceinline__ void ws3_tick_barrier() { asm volatile("bar.sync 0, 384;" ::: "memory"); }
 __device__ __forceinline__ int ws3_last_tick(int nblk) { return nblk + 3; }   // ticks run t = -1 .. nblk + 3
 // Named barrier 1 links MID (arrives, does not wait) and LOOP (waits) once per tick: 64 threads.
 __device__ __forceinline__ void ws3_mid_arrive() { asm volatile("bar.arrive 1, 64;" ::: "memory"); }

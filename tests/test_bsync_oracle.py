@@ -100,6 +100,34 @@ def test_state_machine_matches_reference(call_bits):
 
 
 @needs_ref
+def test_state_machine_random_feeds_match_reference():
+    """randomised: feeds of random length with a random call length each, streams with bit errors, inserted and
+    deleted stretches (slips) -- the restatement must track the reference through every re-acquisition"""
+    rng = np.random.default_rng(77)
+    for trial in range(12):
+        bits = B.downlink_stream(500 + trial, 60, ber=float(rng.choice([0, 1e-3, 1e-2])), glitch_at=tuple(rng.integers(5, 55, 3)))
+        for _ in range(int(rng.integers(0, 3))):                       # delete a stretch: the slot grid jumps backwards
+            p = int(rng.integers(2000, len(bits) - 2000))
+            bits = np.concatenate([bits[:p], bits[p + int(rng.integers(1, 400)):]])
+        P, R = B.PortBsync(1), B.RefBsync(1)
+        pos, total = 0, 0
+        while pos < len(bits):
+            n = int(rng.integers(1, 4000))
+            part = bits[pos:pos + n]
+            pos += len(part)
+            cb = int(rng.integers(1, 511))
+            nb, bu = P.feed(part[None, :], len(part), cb, 16)
+            nr, br, _ = R.feed(part[None, :], len(part), cb, 16)
+            _compare_bursts(nb, bu, nr, br)
+            rs = R.state(0)
+            for f in rs:
+                assert np.array_equal(P.states[0][f], rs[f]), (f, trial, pos, cb)
+            total += int(nb[0])
+        R.close()
+        assert total > 10
+
+
+@needs_ref
 def test_noise_and_constant_input_match_reference():
     rng = np.random.default_rng(5)
     for kind in range(3):
