@@ -500,7 +500,7 @@ int tdm_process_long_batch(tdm_handle* h, const float* iq, int64_t in_stride, in
             if (n < 0) { return done(fail(TDM_ERR_CUDA, "demod kernel launch failed: %s", cudaGetErrorString(cudaGetLastError()))); }
             h->launches += n;
             tdm::launch_stitch_adopt(h->d_seg_dibits, h->seg_stride, h->d_seg_dibits2, h->seg_stride2, d_counts, d_counts2, d_join, d_fixed, d_adopt,
-                                     d_agree, d_mode, d_nforced, mid, K < 512 ? K : 512, d_final, h->d_states, R, S, need2, st);
+                                     d_agree, d_mode, d_nforced, mid, K < 512 ? K : 512, d_final, h->d_states, d_cut, R, S, need2, st);
         }
         // every logical channel continues from the run that produced its last segment's stream
         if (cudaMemcpyAsync(&info->n_forced, d_nforced, sizeof(int), cudaMemcpyDeviceToHost, st) != cudaSuccess) {
@@ -510,7 +510,7 @@ int tdm_process_long_batch(tdm_handle* h, const float* iq, int64_t in_stride, in
     } else {
         tdm::launch_long_last_states(d_carried, h->d_states, C, 1, 0, st);
     }
-    if (S == 1) { TDM_CUDA(cudaMemsetAsync(d_cut, 0, sizeof(int) * (size_t)R, st)); }
+    if (S == 1 && cudaMemsetAsync(d_cut, 0, sizeof(int) * (size_t)R, st) != cudaSuccess) { return done(fail(TDM_ERR_CUDA, "tdm_process_long: memset failed")); }
     tdm::launch_stitch_scan(d_counts, d_cut, d_join, R, S, d_offs, d_totals, st);
     tdm::launch_stitch_copy(h->d_seg_dibits, h->seg_stride, d_counts, d_cut, d_join, d_offs, S, d_out, out_stride, R, need, st);
     // ---- the few samples the equal segments did not cover: sequentially, every channel from its last state (now in d_carried)

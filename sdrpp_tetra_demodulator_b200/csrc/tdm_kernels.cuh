@@ -62,7 +62,8 @@ void launch_stitch_plan(int* join, int* fixed, const int* counts, int n_rows, in
                         int force_all, const tdm_channel_state* final_states, cudaStream_t s);
 void launch_stitch_adopt(uint8_t* dib, long long stride, const uint8_t* dib2, long long stride2, int* counts, const int* counts2, int* join,
                          int* fixed, const int* adopt, int* agree, int* mode, int* n_forced, int force_at, int K,
-                         tdm_channel_state* final_states, const tdm_channel_state* run_states, int n_rows, int S, long long max_len, cudaStream_t s);
+                         tdm_channel_state* final_states, const tdm_channel_state* run_states, int* cut, int n_rows, int S, long long max_len,
+                         cudaStream_t s);
 void launch_stitch_scan(const int* counts, const int* cut, const int* join, int n_rows, int S, long long* offs, long long* totals, cudaStream_t s);
 void launch_stitch_copy(const uint8_t* dib, long long stride, const int* counts, const int* cut, const int* join, const long long* offs, int S,
                         uint8_t* out, long long out_stride, int n_rows, long long max_len, cudaStream_t s);

@@ -162,7 +162,7 @@ __global__ void stitch_decide_kernel(int* __restrict__ join, int* __restrict__ f
 __global__ void stitch_adopt_kernel(uint8_t* __restrict__ dib, long long stride, const uint8_t* __restrict__ dib2, long long stride2,
                                     int* __restrict__ counts, const int* __restrict__ counts2, int* __restrict__ join, int* __restrict__ fixed,
                                     const int* __restrict__ mode, tdm_channel_state* __restrict__ final_states,
-                                    const tdm_channel_state* __restrict__ run_states) {
+                                    const tdm_channel_state* __restrict__ run_states, int* __restrict__ cut, int n_rows) {
     const int c = blockIdx.y;
     if (mode[c] != 1) { return; }
     const int len = counts2[c];
@@ -175,7 +175,14 @@ __global__ void stitch_adopt_kernel(uint8_t* __restrict__ dib, long long stride,
         }
     }
     __syncthreads();
-    if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) { counts[c] = len; join[c] = 0; fixed[c] = 1; }
+    if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) {
+        counts[c] = len; join[c] = 0; fixed[c] = 1;
+        // a successor that joined this row's EXTENDED old stream late has to look again: that stream is gone
+        if (cut[c] > 0) {
+            cut[c] = 0;
+            if (c + 1 < n_rows && fixed[c + 1] == 3) { fixed[c + 1] = 0; join[c + 1] = -1; }
+        }
+    }
 }
 
 // lengths of every segment's contribution and their exclusive offsets inside the channel's output row; per-channel totals
@@ -254,11 +261,12 @@ void launch_stitch_plan(int* join, int* fixed, const int* counts, int n_rows, in
 }
 void launch_stitch_adopt(uint8_t* dib, long long stride, const uint8_t* dib2, long long stride2, int* counts, const int* counts2, int* join,
                          int* fixed, const int* adopt, int* agree, int* mode, int* n_forced, int force_at, int K,
-                         tdm_channel_state* final_states, const tdm_channel_state* run_states, int n_rows, int S, long long max_len, cudaStream_t s) {
+                         tdm_channel_state* final_states, const tdm_channel_state* run_states, int* cut, int n_rows, int S, long long max_len,
+                         cudaStream_t s) {
     stitch_verify_kernel<<<(n_rows + 3) / 4, 128, 0, s>>>(dib, stride, dib2, stride2, counts, counts2, adopt, n_rows, K, agree);
     stitch_decide_kernel<<<1, 32, 0, s>>>(join, fixed, counts, adopt, agree, n_rows, S, force_at, mode, n_forced);
     stitch_adopt_kernel<<<dim3(blocks_for(max_len, 256, 256), (unsigned)n_rows), 256, 0, s>>>(dib, stride, dib2, stride2, counts, counts2, join, fixed,
-                                                                                              mode, final_states, run_states);
+                                                                                              mode, final_states, run_states, cut, n_rows);
 }
 void launch_stitch_scan(const int* counts, const int* cut, const int* join, int n_rows, int S, long long* offs, long long* totals, cudaStream_t s) {
     const int C = n_rows / S;
