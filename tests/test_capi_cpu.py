@@ -129,3 +129,23 @@ def test_burst_demux_is_host_only_and_matches_the_restatement(pkg):
         assert len(mine) == len(ref) and len(mine) in (2, 3)
         for f in ["type", "blk_num", "n_bits", "bits"]:
             assert np.array_equal(mine[f], ref[f]), (typ, f)
+
+
+def test_headers_are_plain_c_and_the_example_fails_loudly_without_a_gpu(pkg, tmp_path):
+    """the boundary is a C ABI: both headers must compile as C11 with -pedantic, and a plain-C host linking the
+    library stops at tdm_create with TDM_ERR_NO_DEVICE when there is no B200 (no CPU fallback behind the ABI)"""
+    import shutil
+    import subprocess
+    import torch
+    if not shutil.which("gcc"):
+        pytest.skip("gcc not on PATH")
+    exe = tmp_path / "demod_then_bursts"
+    libdir = os.path.dirname(pkg.capi.LIB_PATH)
+    r = subprocess.run(["gcc", "-std=c11", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", os.path.join(ROOT, "include"),
+                        os.path.join(ROOT, "examples", "demod_then_bursts.c"), "-L", libdir, "-ltdm_b200", f"-Wl,-rpath,{libdir}", "-o", str(exe)],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    if torch.cuda.is_available():
+        return
+    r = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert r.returncode == 3 and "no CPU fallback" in r.stderr, (r.returncode, r.stderr)
