@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define TDM_ABI_VERSION 1
+#define TDM_ABI_VERSION 2
 
 /* Fixed design sizes of the reference chain (src/main.cpp:35-44,
  * src/dsp/complex_fd.h:30: 128 phases x 8 taps). */
@@ -59,6 +59,17 @@ typedef enum tdm_mem_kind {
 #define TDM_OUT_SYMBOLS 1u  /* complex symbols, PI4DQPSK `out` stream  (src/dsp/pi4dqpsk.h:67)          */
 #define TDM_OUT_DIBITS  2u  /* one dibit per byte, DQPSKSymbolExtractor `out` (src/dsp/dqpsk_sym_extr.cpp:34-51) */
 #define TDM_OUT_BITS    4u  /* one bit per byte, BitUnpacker `out`     (src/dsp/bit_unpacker.cpp:4-10)   */
+#define TDM_OUT_PACKED  8u  /* the same dibits four per byte, first symbol in bits 7..6, last byte zero padded:
+                               what travels between GPUs (tdm_gather_packed) -- written by the slicer itself,
+                               no second pass over the dibits.  tdm_process_io only.                          */
+
+/* tdm_config.flags.  complex_t::fastAmplitude() (used by the FLL's band-edge error, src/dsp/fll.cpp:143) lives
+ * in SDR++ core, which the reference neither vendors nor pins.  Its recalled form is a=|re|, b=|im|,
+ * a>b ? a+0.4b : b+0.4a; the other reading of upstream takes BOTH operands from |re| (so it returns
+ * 1.4|re|).  The bits that come out differ only while the FLL pulls in, but the float trajectories
+ * differ everywhere, so both are built, pinned against the reference compiled the same way
+ * (oracle/_ref/libtetra_ref.so / libtetra_ref_reonly.so) and selectable here. */
+#define TDM_CFG_FASTAMP_RE_ONLY 1
 
 /* The arguments of dsp::demod::PI4DQPSK::init (src/dsp/pi4dqpsk.h:36), same order
  * and meaning.  tdm_default_config fills in what src/main.cpp:35-44,78-84 passes. */
@@ -66,7 +77,7 @@ typedef struct tdm_config {
     double symbolrate;
     double samplerate;
     int32_t rrc_tap_count;
-    int32_t reserved0;
+    int32_t flags;           /* TDM_CFG_* bits; 0 = the behaviour SURVEY.md Appendix A records */
     double rrc_beta;
     double agc_rate;
     double costas_bandwidth;
@@ -82,7 +93,7 @@ typedef struct tdm_config {
  * Exposed so tests can pin the design against the reference's own tables. */
 typedef struct tdm_design {
     int32_t ntaps;                       /* rrc_tap_count, <= TDM_MAX_TAPS                     */
-    int32_t reserved0;
+    int32_t fastamp_re_only;             /* tdm_config.flags & TDM_CFG_FASTAMP_RE_ONLY          */
     float rrc[TDM_MAX_TAPS];             /* matched filter taps, oldest-sample-first           */
     float be_a[TDM_MAX_TAPS];            /* band-edge taps: hbe = a + j b, lbe = a - j b        */
     float be_b[TDM_MAX_TAPS];
@@ -112,7 +123,10 @@ typedef struct tdm_channel_state {
     float err_partial;                   /* sum of the current (unfinished) block of 256        */
     float standarderr;                   /* DQPSKSymbolExtractor::standarderr                   */
     uint32_t sync;                       /* DQPSKSymbolExtractor::sync                          */
-    uint32_t reserved0;
+    uint32_t fll_quad;                   /* with fll_r: the FLL phase reduced for the next sample, */
+                                         /* fll_phase = fll_quad * pi/2 + fll_r (mod 2 pi); see   */
+                                         /* DESIGN.md "canonical order" (the NCO's range reduction */
+                                         /* is prepared one sample ahead)                          */
     uint64_t n_samples;                  /* lifetime input samples                              */
     uint64_t n_symbols;                  /* lifetime output symbols                             */
     float err_blocks[TDM_SYNC_BLOCKS];   /* completed block sums, slot = err_ptr / 256          */
@@ -120,7 +134,8 @@ typedef struct tdm_channel_state {
                                          /* delay line behind lbe/hbe/RRC FIRs (fll.cpp:141-142, */
                                          /* pi4dqpsk.cpp:135-136)                                */
     float r_hist[2 * (TDM_INTERP_TAPS - 1)]; /* last 7 RRC outputs (complex_fd.cpp:148)          */
-    float reserved1[2];
+    float fll_r;
+    float reserved1;
 } tdm_channel_state;
 
 /* GUI-facing numbers the plugin reads from the slicer (src/main.cpp:211-217). */
@@ -174,6 +189,19 @@ int64_t tdm_max_symbols(const tdm_handle* h, int64_t count);
 int tdm_process(tdm_handle* h, const float* iq, int64_t in_stride, int32_t count,
                 float* syms, uint8_t* dibits, uint8_t* bits, int64_t out_stride,
                 int32_t* out_counts, uint32_t out_flags, int32_t mem_kind);
+
+/* tdm_process with its arguments in a struct, plus the packed output (TDM_OUT_PACKED):
+ *   packed : [C][packed_stride] bytes, packed_stride >= tdm_max_symbols(count) / 4 (tdm_max_symbols is a multiple of 16);
+ *            byte j of a row holds symbols 4j .. 4j+3 of this call.
+ * Unused members must be zero. */
+typedef struct tdm_io {
+    const float* iq; int64_t in_stride; int32_t count; int32_t mem_kind;
+    float* syms; uint8_t* dibits; uint8_t* bits; uint8_t* packed;
+    int64_t out_stride, packed_stride;
+    int32_t* out_counts;
+    uint32_t out_flags; uint32_t reserved;
+} tdm_io;
+int tdm_process_io(tdm_handle* h, const tdm_io* io);
 
 /* ONE long capture of ONE channel, demodulated as up to n_channels overlapping time segments in parallel (SURVEY.md
  * section 8f rank 4; BASELINE.json configs[1] "1 channel, 1e9 complex samples").  The chain is a recurrence in
@@ -244,6 +272,15 @@ int64_t tdm_launch_count(const tdm_handle* h);
  * counts [C].  Device pointers; asynchronous on the handle's stream. */
 int tdm_pack_dibits(tdm_handle* h, const uint8_t* dibits, int64_t in_stride, const int32_t* counts,
                     uint8_t* packed, int64_t out_stride);
+
+/* The inverse, on the receiving side of the gather: packed rows -> one dibit per byte (DQPSKSymbolExtractor's
+ * stream, dibits may be NULL) and/or one bit per byte, high bit first (BitUnpacker::process,
+ * src/dsp/bit_unpacker.cpp:4-10: the stream the plugin's network sink sends, src/main.cpp:385-389; bits may be
+ * NULL).  packed [n_rows][in_stride], counts [n_rows] symbols per row, dibits [n_rows][dibit_stride], bits
+ * [n_rows][bit_stride], max_symbols = upper bound of counts.  n_rows need not be the handle's channel count
+ * (rank 0 unpacks every rank's rows).  Device pointers; asynchronous on the handle's stream. */
+int tdm_unpack_dibits(tdm_handle* h, const uint8_t* packed, int64_t in_stride, const int32_t* counts, int32_t n_rows,
+                      uint8_t* dibits, int64_t dibit_stride, uint8_t* bits, int64_t bit_stride, int64_t max_symbols);
 
 /* Deterministic synthetic TETRA-mapped pi/4-DQPSK capture, generated on the
  * device: channel c uses data seed seed_data+c and noise seed

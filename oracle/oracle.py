@@ -17,6 +17,8 @@ import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 REF_SO = os.path.join(HERE, "_ref", "libtetra_ref.so")
+REF_SO_REONLY = os.path.join(HERE, "_ref", "libtetra_ref_reonly.so")   # fastAmplitude() with both operands from |re|
+TDM_CFG_FASTAMP_RE_ONLY = 1
 
 TDM_MAX_TAPS = 65
 TDM_HIST = 64
@@ -28,7 +30,7 @@ TDM_SYNC_BLOCKS = 16
 class TdmConfig(C.Structure):
     _fields_ = [
         ("symbolrate", C.c_double), ("samplerate", C.c_double),
-        ("rrc_tap_count", C.c_int32), ("reserved0", C.c_int32),
+        ("rrc_tap_count", C.c_int32), ("flags", C.c_int32),
         ("rrc_beta", C.c_double), ("agc_rate", C.c_double), ("costas_bandwidth", C.c_double),
         ("fll_bandwidth", C.c_double), ("omega_gain", C.c_double), ("mu_gain", C.c_double),
         ("omega_rel_limit", C.c_double),
@@ -37,7 +39,7 @@ class TdmConfig(C.Structure):
 
 class TdmDesign(C.Structure):
     _fields_ = [
-        ("ntaps", C.c_int32), ("reserved0", C.c_int32),
+        ("ntaps", C.c_int32), ("fastamp_re_only", C.c_int32),
         ("rrc", C.c_float * TDM_MAX_TAPS), ("be_a", C.c_float * TDM_MAX_TAPS), ("be_b", C.c_float * TDM_MAX_TAPS),
         ("bank", (C.c_float * TDM_INTERP_TAPS) * TDM_INTERP_PHASES),
         ("agc_rate", C.c_float), ("agc_set_point", C.c_float), ("agc_max_gain", C.c_float), ("agc_init_gain", C.c_float),
@@ -55,15 +57,15 @@ STATE_DTYPE = np.dtype([
     ("agc_gain", "<f4"), ("fll_phase", "<f4"), ("fll_freq", "<f4"), ("tr_mu", "<f4"), ("tr_omega", "<f4"),
     ("tr_offset", "<i4"), ("costas_phase", "<f4"), ("costas_freq", "<f4"), ("costas_ph2", "<f4"),
     ("prev_sym", "<u4"), ("err_ptr", "<u4"), ("err_disp", "<u4"), ("err_partial", "<f4"),
-    ("standarderr", "<f4"), ("sync", "<u4"), ("reserved0", "<u4"), ("n_samples", "<u8"), ("n_symbols", "<u8"),
+    ("standarderr", "<f4"), ("sync", "<u4"), ("fll_quad", "<u4"), ("n_samples", "<u8"), ("n_symbols", "<u8"),
     ("err_blocks", "<f4", (TDM_SYNC_BLOCKS,)), ("x_hist", "<f4", (2 * TDM_HIST,)),
-    ("r_hist", "<f4", (2 * (TDM_INTERP_TAPS - 1),)), ("reserved1", "<f4", (2,)),
+    ("r_hist", "<f4", (2 * (TDM_INTERP_TAPS - 1),)), ("fll_r", "<f4"), ("reserved1", "<f4"),
 ], align=True)
 
 # fields that must match bit-for-bit between the CUDA path and Oracle B
 EXACT_STATE_FIELDS = ["agc_gain", "fll_phase", "fll_freq", "tr_mu", "tr_omega", "tr_offset", "costas_phase",
                       "costas_freq", "costas_ph2", "prev_sym", "err_ptr", "err_disp", "n_samples", "n_symbols",
-                      "x_hist", "r_hist"]
+                      "x_hist", "r_hist", "fll_quad", "fll_r"]
 # atan2f-derived GUI metric: libm vs CUDA differ in the last place -> tolerance
 METRIC_STATE_FIELDS = ["err_partial", "standarderr", "err_blocks"]
 
@@ -120,6 +122,8 @@ def lib_b() -> C.CDLL:
         L.ob_design.restype = C.c_int
         L.ob_state_init.argtypes = [C.POINTER(TdmDesign), C.c_void_p]
         L.ob_sincos.argtypes = [C.c_float, C.POINTER(C.c_float), C.POINTER(C.c_float)]
+        L.ob_fll_nco.argtypes = [C.c_float, C.c_float, C.c_float, C.POINTER(C.c_float), C.POINTER(C.c_float)]
+        L.ob_fll_fallback_count.restype = C.c_long
         L.ob_process.argtypes = [C.POINTER(TdmDesign), C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p,
                                  C.c_void_p]
         L.ob_process.restype = C.c_int64
@@ -165,9 +169,11 @@ def tx_dibits(channel: int, n_symbols: int, seed_data: int = 12345, k0: int = 0)
 class OracleB:
     """Canonical-order restatement, C channels with carried state."""
 
-    def __init__(self, n_channels: int = 1, config: TdmConfig | None = None):
+    def __init__(self, n_channels: int = 1, config: TdmConfig | None = None, fastamp_re_only: bool = False):
         self.L = lib_b()
         self.cfg = config or self.default_config()
+        if fastamp_re_only:
+            self.cfg.flags |= TDM_CFG_FASTAMP_RE_ONLY
         self.design = TdmDesign()
         rc = self.L.ob_design(C.byref(self.cfg), C.byref(self.design))
         if rc != 0:
@@ -198,20 +204,29 @@ class OracleB:
         return counts, syms, dibits, bits
 
 
+def count_fll_fallbacks(iq: np.ndarray, config: TdmConfig | None = None, fastamp_re_only: bool = False) -> int:
+    """How many samples of `iq` take the classic range reduction in the FLL's NCO (oracle_b.c ob_fll_reduce)."""
+    L = lib_b()
+    n0 = L.ob_fll_fallback_count()
+    OracleB(iq.shape[0], config, fastamp_re_only=fastamp_re_only).process(iq, want_syms=False)
+    return int(L.ob_fll_fallback_count() - n0)
+
+
 # --------------------------------------------------------------------------- Oracle A
-def have_ref() -> bool:
-    return os.path.exists(REF_SO)
+def have_ref(fastamp_re_only: bool = False) -> bool:
+    return os.path.exists(REF_SO_REONLY if fastamp_re_only else REF_SO)
 
 
-_LIB_A = None
+_LIB_A = {}
 
 
-def lib_a() -> C.CDLL:
-    global _LIB_A
-    if _LIB_A is None:
-        if not have_ref():
-            raise FileNotFoundError(f"{REF_SO} missing: run `make -C oracle ref` where /root/reference exists")
-        L = C.CDLL(REF_SO)
+def lib_a(fastamp_re_only: bool = False) -> C.CDLL:
+    key = bool(fastamp_re_only)
+    if key not in _LIB_A:
+        path = REF_SO_REONLY if key else REF_SO
+        if not os.path.exists(path):
+            raise FileNotFoundError(f"{path} missing: run `make -C oracle ref` where /root/reference exists")
+        L = C.CDLL(path)
         L.tref_default_params.argtypes = [C.POINTER(TrefParams)]
         L.tref_create.argtypes = [C.POINTER(TrefParams)]
         L.tref_create.restype = C.c_void_p
@@ -226,15 +241,15 @@ def lib_a() -> C.CDLL:
         L.tref_get_coeffs.argtypes = [C.c_void_p, C.c_void_p]
         L.tref_process_multi.argtypes = [C.c_void_p, C.c_int, C.c_int64, C.c_void_p, C.c_void_p, C.c_int64,
                                          C.c_void_p, C.c_int]
-        _LIB_A = L
-    return _LIB_A
+        _LIB_A[key] = L
+    return _LIB_A[key]
 
 
 class OracleA:
     """The reference's own PI4DQPSK -> DQPSKSymbolExtractor -> BitUnpacker chain, one instance per channel."""
 
-    def __init__(self, n_channels: int = 1, params: TrefParams | None = None):
-        self.L = lib_a()
+    def __init__(self, n_channels: int = 1, params: TrefParams | None = None, fastamp_re_only: bool = False):
+        self.L = lib_a(fastamp_re_only)
         self.n_channels = n_channels
         self.handles = [self.L.tref_create(C.byref(params) if params is not None else None)
                         for _ in range(n_channels)]

@@ -25,7 +25,11 @@
  *     lbe taps a-jb (exact conjugates, fll.cpp:89-93)  P = sum a x, Q = sum b x,
  *     hbe = (P.re-Q.im, P.im+Q.re), lbe = (P.re+Q.im, P.im-Q.re);
  *   - sin/cos come from ob_sincos() below (Cody-Waite + degree-7/8 polynomials),
- *     never from libm;
+ *     never from libm; the FLL's NCO (one evaluation per input sample, on the
+ *     sample-rate recurrence) uses the same polynomials on a reduction that is
+ *     PREPARED one sample ahead (ob_fll_prepare / ob_fll_reduce below) so that a
+ *     GPU needs one addition, not a range reduction, between the loop filter and
+ *     the polynomial;
  *   - sqrtf is IEEE-correct on both sides; floorf, comparisons, min/max exact.
  *
  * Each function cites the reference lines it follows (paths relative to
@@ -103,6 +107,7 @@ int ob_design(const tdm_config* cfg, tdm_design* d) {
     int nt = cfg->rrc_tap_count;
     if (nt < 1 || nt > TDM_MAX_TAPS) { return -4; }
     d->ntaps = nt;
+    d->fastamp_re_only = (cfg->flags & TDM_CFG_FASTAMP_RE_ONLY) ? 1 : 0;
     int pad = TDM_MAX_TAPS - nt; /* shorter filters are zero-padded at the OLD end */
 
     /* --- RRC: taps::rootRaisedCosine<float>(n, beta, symrate, samprate)  [A.6], pi4dqpsk.cpp:18 */
@@ -248,11 +253,104 @@ void ob_sincos(float x, float* s, float* c) {
     *c = cc;
 }
 
-/* [A.1] complex_t::fastAmplitude: a=|re|, b=|im|; a>b ? a+0.4b : b+0.4a */
-static inline float ob_fastamp(float re, float im) {
-    float a = fabsf(re), b = fabsf(im);
+/* [A.1] complex_t::fastAmplitude: a=|re|, b=|im|; a>b ? a+0.4b : b+0.4a.
+ * re_only selects the OTHER reading of upstream SDR++ (both operands from |re|, i.e. b = |re| too:
+ * TDM_CFG_FASTAMP_RE_ONLY, include/tdm_b200.h); SDR++ core is not vendored by the reference, so both
+ * readings are built and pinned (oracle/_ref/libtetra_ref_reonly.so is the reference compiled with the
+ * stand-in's -DSDRPP_STANDIN_FASTAMP_RE_ONLY). */
+static inline float ob_fastamp(float re, float im, int re_only) {
+    float a = fabsf(re), b = re_only ? a : fabsf(im);
     float hi = a > b ? a : b, lo = a > b ? b : a;
     return fmaf(0.4f, lo, hi);
+}
+
+/* ---- the FLL's NCO, math::phasor(-pcl.phase) at fll.cpp:137 -------------------------------------------
+ * The reference evaluates cosf/sinf of the loop phase once per input sample, and the phase of sample n+1
+ * depends on the error of sample n: range reduction + polynomial sit on the sample-rate recurrence.  The
+ * canonical order cuts that dependency short without changing what is computed:
+ *   ob_fll_prepare (phi_n, f_n) -> quadrant q and r0 = phi_n - q pi/2, with q the nearest quadrant of the
+ *       PREDICTED next phase phi_n + f_n (what the next phase would be if the frequency did not move);
+ *   after the loop filter:  r = r0 + f_{n+1}   (= the next phase, unwrapped, minus q pi/2);
+ *   ob_fll_reduce: if |r| <= OB_FLL_RMAX the pair (q, r) is used as it is (the frequency moves by
+ *       beta*err ~ 1e-4 per sample, so r overshoots pi/4 by about that much at most: the polynomials below
+ *       are as accurate there); otherwise -- the frequency jumped, e.g. a burst after silence with the AGC
+ *       gain wide open -- (q, r) come from the classic reduction of the wrapped phase.
+ * Deviation from sin/cos of the wrapped phase: the polynomial error (< 3e-7 absolute for |r| <= 0.8) plus,
+ * in the one sample where the phase wraps, 2*pi_f - 2*pi = 1.7e-7 rad (the wrap subtracts the FLOAT 2 pi like
+ * the reference, the quadrant arithmetic uses pi/2 to 2^-48).  (q, r) travel in tdm_channel_state
+ * (fll_quad, fll_r), so chunking cannot change a bit. */
+#define OB_FLL_RMAX 0.8f
+static const float ob_two_over_pi = 0.636619747f, ob_magic = 12582912.0f /* 1.5 * 2^23 */;
+static const float ob_pio2_hi = 1.57079637f, ob_pio2_lo = -4.37113883e-8f;
+
+static inline void ob_fll_prepare(float phi, float f, uint32_t* q, float* r0) {
+    float t = fmaf(phi + f, ob_two_over_pi, ob_magic);
+    uint32_t u; memcpy(&u, &t, 4);
+    float qf = t - ob_magic;
+    float r = fmaf(qf, -ob_pio2_hi, phi);
+    *r0 = fmaf(qf, -ob_pio2_lo, r);
+    *q = u & 3u;
+}
+
+static long ob_fallbacks;   /* how often the classic reduction was taken (tests want to know they exercised it) */
+long ob_fll_fallback_count(void) { return __atomic_load_n(&ob_fallbacks, __ATOMIC_RELAXED); }
+
+static inline void ob_fll_reduce(float phi_wrapped, uint32_t* q, float* r) {
+    if (!(fabsf(*r) <= OB_FLL_RMAX)) {
+        __atomic_fetch_add(&ob_fallbacks, 1, __ATOMIC_RELAXED);
+        float t = fmaf(phi_wrapped, ob_two_over_pi, ob_magic);
+        uint32_t u; memcpy(&u, &t, 4);
+        float qf = t - ob_magic;
+        float rr = fmaf(qf, -ob_pio2_hi, phi_wrapped);
+        *r = fmaf(qf, -ob_pio2_lo, rr);
+        *q = u & 3u;
+    }
+}
+
+/* sin r, cos r for the reduced argument: sin as in ob_sincos; cos with the same coefficients in Estrin
+ * form (one dependent level less): 1 + r2 ((-1/2 + C1 r2) + r4 (C2 + C3 r2)). */
+static inline void ob_fll_poly(float r, float* sn, float* cs) {
+    const float S1 = -1.6666654611e-1f, S2 = 8.3321608736e-3f, S3 = -1.9515295891e-4f;
+    const float C1 = 4.166664568298827e-2f, C2 = -1.388731625493765e-3f, C3 = 2.443315711809948e-5f;
+    float r2 = r * r;
+    float sp = fmaf(r2, S3, S2);
+    sp = fmaf(sp, r2, S1);
+    *sn = fmaf(sp, r2 * r, r);
+    float r4 = r2 * r2;
+    float cl = fmaf(C1, r2, -0.5f), ch = fmaf(C3, r2, C2);
+    float cq = fmaf(ch, r4, cl);
+    *cs = fmaf(cq, r2, 1.0f);
+}
+
+/* The NCO exactly as one step of the chain evaluates it, for the accuracy test: state (phi, f_old) before the
+ * loop update, f_new after it; returns sin/cos of the new phase wrap(phi + f_new) as the next sample will use
+ * them, with the quadrant folded back in. */
+void ob_fll_nco(float phi, float f_old, float f_new, float* s, float* c) {
+    const float pi = OB_FL_M_PI, two_pi = pi - (-pi);
+    uint32_t q; float r0;
+    ob_fll_prepare(phi, f_old, &q, &r0);
+    float r = r0 + f_new;
+    float ph = phi + f_new;
+    while (ph > pi) { ph -= two_pi; }
+    while (ph < -pi) { ph += two_pi; }
+    ob_fll_reduce(ph, &q, &r);
+    float sn, cs;
+    ob_fll_poly(r, &sn, &cs);
+    float ss = (q & 1u) ? cs : sn, cc = (q & 1u) ? sn : cs;
+    if (q & 2u) { ss = -ss; }
+    if ((q + 1u) & 2u) { cc = -cc; }
+    *s = ss; *c = cc;
+}
+
+/* (yr, yi) * (-j)^q: the quadrant part of exp(-j phi) applied to the sample (exact) */
+static inline void ob_quarter_turns(uint32_t q, float* yr, float* yi) {
+    float a = *yr, b = *yi;
+    switch (q & 3u) {
+        case 1: *yr = b; *yi = -a; break;
+        case 2: *yr = -a; *yi = -b; break;
+        case 3: *yr = -b; *yi = a; break;
+        default: break;
+    }
 }
 
 static inline float ob_clampf(float v, float lo, float hi) { return v > hi ? hi : (v < lo ? lo : v); }
@@ -277,7 +375,9 @@ static int64_t ob_process_chunk(const tdm_design* d, tdm_channel_state* s, ob_wo
     const float costas_two_pi = 2 * OB_FL_M_PI;         /* pi4dqpsk_costas.cpp:11-15 */
     const float quarter_pi = OB_FL_M_PI / 4.0f;         /* pi4dqpsk_costas.cpp:10 */
     float g = s->agc_gain;
-    float fph = s->fll_phase, ffr = s->fll_freq;
+    float fph = s->fll_phase, ffr = s->fll_freq, fr = s->fll_r;
+    uint32_t fq = s->fll_quad;
+    const int re_only = d->fastamp_re_only != 0;
     float mu = s->tr_mu, om = s->tr_omega;
     int offset = s->tr_offset;
     float cph = s->costas_phase, cfr = s->costas_freq, ph2 = s->costas_ph2;
@@ -294,11 +394,16 @@ static int64_t ob_process_chunk(const tdm_design* d, tdm_channel_state* s, ob_wo
         g = fmaf(d->agc_set_point - amp, d->agc_rate, g);
         if (g > d->agc_max_gain) { g = d->agc_max_gain; }
 
-        /* ---- FLL: fll.cpp:135-149.  shift = phasor(-phase) = (cos, -sin) */
+        /* ---- FLL: fll.cpp:135-149.  shift = phasor(-phase) = (cos, -sin) = (-j)^q (cos r, -sin r) */
         float sn, cs;
-        ob_sincos(fph, &sn, &cs);
-        float xr = fmaf(yr, cs, yi * sn);
-        float xi = fmaf(yi, cs, -(yr * sn));
+        ob_fll_poly(fr, &sn, &cs);
+        float tr = yr, ti = yi;
+        ob_quarter_turns(fq, &tr, &ti);
+        float xr = fmaf(tr, cs, ti * sn);
+        float xi = fmaf(ti, cs, -(tr * sn));
+        /* next sample's reduction, from the state BEFORE the loop update */
+        uint32_t nq; float r0;
+        ob_fll_prepare(fph, ffr, &nq, &r0);
         float* win = &w->x[2 * n];          /* win[0..63] history, win[64] = x */
         win[2 * TDM_HIST] = xr;
         win[2 * TDM_HIST + 1] = xi;
@@ -312,14 +417,17 @@ static int64_t ob_process_chunk(const tdm_design* d, tdm_channel_state* s, ob_wo
             rr = fmaf(d->rrc[k], vr, rr);   /* RRC matched filter, pi4dqpsk.cpp:136, [A.4] */
             ri = fmaf(d->rrc[k], vi, ri);
         }
-        float hbe = ob_fastamp(pr - qi, pim + qr);
-        float lbe = ob_fastamp(pr + qi, pim - qr);
+        float hbe = ob_fastamp(pr - qi, pim + qr, re_only);
+        float lbe = ob_fastamp(pr + qi, pim - qr, re_only);
         float ferr = hbe - lbe;             /* fll.cpp:143 */
         /* pcl.advance, alpha = 0 (fll.cpp:25,145) [A.2] */
         ffr = ob_clampf(fmaf(d->fll_beta, ferr, ffr), d->fll_min_freq, d->fll_max_freq);
+        fr = r0 + ffr;
         fph = fph + ffr;
         while (fph > pi) { fph -= two_pi; }
         while (fph < -pi) { fph += two_pi; }
+        fq = nq;
+        ob_fll_reduce(fph, &fq, &fr);
 
         float* rb = &w->r[2 * n];           /* rb[0..6] previous RRC outputs, rb[7] = this one */
         rb[2 * (TDM_INTERP_TAPS - 1)] = rr;
@@ -410,7 +518,7 @@ static int64_t ob_process_chunk(const tdm_design* d, tdm_channel_state* s, ob_wo
     memcpy(s->x_hist, &w->x[2 * count], sizeof(s->x_hist));                                    /* [A.4] memmove */
     memcpy(s->r_hist, &w->r[2 * count], sizeof(s->r_hist));                                    /* complex_fd.cpp:148 */
     s->agc_gain = g;
-    s->fll_phase = fph; s->fll_freq = ffr;
+    s->fll_phase = fph; s->fll_freq = ffr; s->fll_quad = fq; s->fll_r = fr;
     s->tr_mu = mu; s->tr_omega = om; s->tr_offset = offset;
     s->costas_phase = cph; s->costas_freq = cfr; s->costas_ph2 = ph2;
     s->prev_sym = prev;

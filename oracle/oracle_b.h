@@ -14,6 +14,8 @@ void ob_default_config(tdm_config* cfg);
 int ob_design(const tdm_config* cfg, tdm_design* d);
 void ob_state_init(const tdm_design* d, tdm_channel_state* s);
 void ob_sincos(float x, float* s, float* c);
+void ob_fll_nco(float phi, float f_old, float f_new, float* s, float* c);
+long ob_fll_fallback_count(void);
 
 /* One channel.  syms/dibits/bits may be NULL.  Returns symbols emitted. */
 int64_t ob_process(const tdm_design* d, tdm_channel_state* s, const float* iq, int64_t count,

@@ -11,7 +11,7 @@ import os
 import numpy as np
 
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(PKG_DIR, "libtdm_b200.so")
+LIB_PATH = os.environ.get("TDM_LIB_OVERRIDE") or os.path.join(PKG_DIR, "libtdm_b200.so")   # override: development A/B builds only
 
 TDM_MAX_TAPS = 65
 TDM_HIST = 64
@@ -33,6 +33,8 @@ TDM_MEM_DEVICE = 1
 TDM_OUT_SYMBOLS = 1
 TDM_OUT_DIBITS = 2
 TDM_OUT_BITS = 4
+TDM_OUT_PACKED = 8
+TDM_CFG_FASTAMP_RE_ONLY = 1
 
 # every symbol include/tdm_b200.h declares (tests check the library exports each one)
 EXPORTED_SYMBOLS = [
@@ -40,7 +42,7 @@ EXPORTED_SYMBOLS = [
     "tdm_max_symbols", "tdm_process", "tdm_reset", "tdm_reset_all", "tdm_get_state", "tdm_set_state",
     "tdm_get_metrics", "tdm_set_config", "tdm_get_design", "tdm_set_kernel_variant", "tdm_last_kernel_ms",
     "tdm_launch_count", "tdm_pack_dibits", "tdm_synth_capture", "tdm_last_error", "tdm_abi_version",
-    "tdm_process_long", "tdm_process_long_batch",
+    "tdm_process_long", "tdm_process_long_batch", "tdm_process_io", "tdm_unpack_dibits",
 ]
 # ... and include/tdm_burst_b200.h
 EXPORTED_BURST_SYMBOLS = [
@@ -59,7 +61,7 @@ class TdmConfig(C.Structure):
     """tdm_config: the arguments of dsp::demod::PI4DQPSK::init (src/dsp/pi4dqpsk.h:36)."""
     _fields_ = [
         ("symbolrate", C.c_double), ("samplerate", C.c_double),
-        ("rrc_tap_count", C.c_int32), ("reserved0", C.c_int32),
+        ("rrc_tap_count", C.c_int32), ("flags", C.c_int32),
         ("rrc_beta", C.c_double), ("agc_rate", C.c_double), ("costas_bandwidth", C.c_double),
         ("fll_bandwidth", C.c_double), ("omega_gain", C.c_double), ("mu_gain", C.c_double),
         ("omega_rel_limit", C.c_double),
@@ -68,7 +70,7 @@ class TdmConfig(C.Structure):
 
 class TdmDesign(C.Structure):
     _fields_ = [
-        ("ntaps", C.c_int32), ("reserved0", C.c_int32),
+        ("ntaps", C.c_int32), ("fastamp_re_only", C.c_int32),
         ("rrc", C.c_float * TDM_MAX_TAPS), ("be_a", C.c_float * TDM_MAX_TAPS), ("be_b", C.c_float * TDM_MAX_TAPS),
         ("bank", (C.c_float * TDM_INTERP_TAPS) * TDM_INTERP_PHASES),
         ("agc_rate", C.c_float), ("agc_set_point", C.c_float), ("agc_max_gain", C.c_float), ("agc_init_gain", C.c_float),
@@ -101,9 +103,9 @@ STATE_DTYPE = np.dtype([
     ("agc_gain", "<f4"), ("fll_phase", "<f4"), ("fll_freq", "<f4"), ("tr_mu", "<f4"), ("tr_omega", "<f4"),
     ("tr_offset", "<i4"), ("costas_phase", "<f4"), ("costas_freq", "<f4"), ("costas_ph2", "<f4"),
     ("prev_sym", "<u4"), ("err_ptr", "<u4"), ("err_disp", "<u4"), ("err_partial", "<f4"),
-    ("standarderr", "<f4"), ("sync", "<u4"), ("reserved0", "<u4"), ("n_samples", "<u8"), ("n_symbols", "<u8"),
+    ("standarderr", "<f4"), ("sync", "<u4"), ("fll_quad", "<u4"), ("n_samples", "<u8"), ("n_symbols", "<u8"),
     ("err_blocks", "<f4", (TDM_SYNC_BLOCKS,)), ("x_hist", "<f4", (2 * TDM_HIST,)),
-    ("r_hist", "<f4", (2 * (TDM_INTERP_TAPS - 1),)), ("reserved1", "<f4", (2,)),
+    ("r_hist", "<f4", (2 * (TDM_INTERP_TAPS - 1),)), ("fll_r", "<f4"), ("reserved1", "<f4"),
 ], align=True)
 # numpy views of tdm_burst / tdm_bsync_state / tdm_tp_sap_block (include/tdm_burst_b200.h)
 BURST_DTYPE = np.dtype([("bitnum", "<u4"), ("train_seq", "<i4"), ("tn", "<u4"), ("fn", "<u4"), ("mn", "<u4"),
@@ -119,6 +121,14 @@ BSYNC_STATE_DTYPE = np.dtype([("state", "<i4"), ("bits_in_buf", "<u4"), ("bitbuf
 TP_SAP_BLOCK_DTYPE = np.dtype([("type", "<i4"), ("blk_num", "<i4"), ("n_bits", "<i4"), ("bits", "u1", (432,))], align=True)
 METRICS_DTYPE = np.dtype([("standarderr", "<f4"), ("sync", "<u4"), ("n_samples", "<u8"), ("n_symbols", "<u8")],
                          align=True)
+
+
+class TdmIo(C.Structure):
+    """tdm_io (include/tdm_b200.h)"""
+    _fields_ = [("iq", C.c_void_p), ("in_stride", C.c_int64), ("count", C.c_int32), ("mem_kind", C.c_int32),
+                ("syms", C.c_void_p), ("dibits", C.c_void_p), ("bits", C.c_void_p), ("packed", C.c_void_p),
+                ("out_stride", C.c_int64), ("packed_stride", C.c_int64), ("out_counts", C.c_void_p),
+                ("out_flags", C.c_uint32), ("reserved", C.c_uint32)]
 
 
 class TdmError(RuntimeError):
@@ -149,6 +159,8 @@ def lib() -> C.CDLL:
         "tdm_set_stream": (C.c_int, [vp, vp]),
         "tdm_max_symbols": (i64, [vp, i64]),
         "tdm_process": (C.c_int, [vp, vp, i64, i32, vp, vp, vp, i64, vp, u32, i32]),
+        "tdm_process_io": (C.c_int, [vp, C.POINTER(TdmIo)]),
+        "tdm_unpack_dibits": (C.c_int, [vp, vp, i64, vp, i32, vp, i64, vp, i64, i64]),
         "tdm_reset": (C.c_int, [vp]),
         "tdm_reset_all": (C.c_int, [vp]),
         "tdm_get_state": (C.c_int, [vp, vp, i32]),

@@ -76,6 +76,7 @@ struct tdm_handle {
     float2* d_syms = nullptr;
     uint8_t* d_dibits = nullptr;
     uint8_t* d_bits = nullptr;
+    uint8_t* d_packed = nullptr;
     int* d_counts = nullptr;
     // tdm_process_long: the logical channel's carried state [0] + a freshly initialised state [1]; per-segment scratch
     tdm_channel_state* d_long_state = nullptr;   // [n_channels + 1]: carried state per logical channel, then one fresh state
@@ -100,11 +101,15 @@ void fill_params(const tdm_handle* h, tdm::DemodParams& p) {
     p.tr_alpha = d.tr_alpha; p.tr_beta = d.tr_beta; p.tr_min_omega = d.tr_min_omega; p.tr_max_omega = d.tr_max_omega;
     p.costas_alpha = d.costas_alpha; p.costas_beta = d.costas_beta;
     p.costas_min_freq = d.costas_min_freq; p.costas_max_freq = d.costas_max_freq;
+    p.fastamp_re_only = d.fastamp_re_only;
+    p.packed = nullptr;
+    p.packed_stride = 0;
     p.bank = h->d_bank;
     p.n_channels = h->n_channels;
     p.states = h->d_states;
     p.rows_per_channel = 1;
     p.channel_stride = 0;
+    p.debug_mask = 0;
 }
 
 void init_state(const tdm_design& d, tdm_channel_state& s) {
@@ -136,6 +141,7 @@ int ensure_staging(tdm_handle* h, uint32_t flags) {
     if ((flags & TDM_OUT_SYMBOLS) && !h->d_syms) { TDM_CUDA(cudaMalloc(&h->d_syms, sizeof(float2) * C * (size_t)h->max_syms)); }
     if ((flags & TDM_OUT_DIBITS) && !h->d_dibits) { TDM_CUDA(cudaMalloc(&h->d_dibits, C * (size_t)h->max_syms)); }
     if ((flags & TDM_OUT_BITS) && !h->d_bits) { TDM_CUDA(cudaMalloc(&h->d_bits, 2 * C * (size_t)h->max_syms)); }
+    if ((flags & TDM_OUT_PACKED) && !h->d_packed) { TDM_CUDA(cudaMalloc(&h->d_packed, C * (size_t)(h->max_syms / 4))); }
     return TDM_OK;
 }
 
@@ -199,7 +205,7 @@ int tdm_destroy(tdm_handle* h) {
     DeviceGuard guard(h->device);
     if (h->own_stream) { cudaStreamSynchronize(h->own_stream); }
     cudaFree(h->d_bank); cudaFree(h->d_states); cudaFree(h->d_iq); cudaFree(h->d_syms);
-    cudaFree(h->d_dibits); cudaFree(h->d_bits); cudaFree(h->d_counts);
+    cudaFree(h->d_dibits); cudaFree(h->d_bits); cudaFree(h->d_packed); cudaFree(h->d_counts);
     cudaFree(h->d_long_state); cudaFree(h->d_states2); cudaFree(h->d_seg_dibits); cudaFree(h->d_seg_dibits2);
     cudaFree(h->d_seg_ints); cudaFree(h->d_offs);
     if (h->ev_start) { cudaEventDestroy(h->ev_start); }
@@ -224,17 +230,39 @@ int64_t tdm_max_symbols(const tdm_handle* h, int64_t count) {
 
 int tdm_process(tdm_handle* h, const float* iq, int64_t in_stride, int32_t count, float* syms, uint8_t* dibits,
                 uint8_t* bits, int64_t out_stride, int32_t* out_counts, uint32_t out_flags, int32_t mem_kind) {
-    if (!h) { return fail(TDM_ERR_ARG, "tdm_process: null handle"); }
+    if (out_flags & TDM_OUT_PACKED) { return fail(TDM_ERR_ARG, "tdm_process: TDM_OUT_PACKED needs tdm_process_io (it carries the packed buffer)"); }
+    tdm_io io;
+    std::memset(&io, 0, sizeof(io));
+    io.iq = iq; io.in_stride = in_stride; io.count = count;
+    io.syms = syms; io.dibits = dibits; io.bits = bits; io.out_stride = out_stride;
+    io.out_counts = out_counts; io.out_flags = out_flags; io.mem_kind = mem_kind;
+    return tdm_process_io(h, &io);
+}
+
+int tdm_process_io(tdm_handle* h, const tdm_io* io) {
+    if (!h || !io) { return fail(TDM_ERR_ARG, "tdm_process: null handle / io"); }
+    const float* iq = io->iq;
+    const int64_t in_stride = io->in_stride, out_stride = io->out_stride, packed_stride = io->packed_stride;
+    const int32_t count = io->count, mem_kind = io->mem_kind;
+    float* syms = io->syms;
+    uint8_t *dibits = io->dibits, *bits = io->bits, *packed = io->packed;
+    int32_t* out_counts = io->out_counts;
+    const uint32_t out_flags = io->out_flags;
     if (count < 0) { return fail(TDM_ERR_ARG, "tdm_process: negative count"); }
     if (!out_counts) { return fail(TDM_ERR_ARG, "tdm_process: out_counts is null"); }
     if (count > 0 && !iq) { return fail(TDM_ERR_ARG, "tdm_process: iq is null"); }
     if (in_stride < count) { return fail(TDM_ERR_ARG, "tdm_process: in_stride < count"); }
-    if (((out_flags & TDM_OUT_SYMBOLS) && !syms) || ((out_flags & TDM_OUT_DIBITS) && !dibits) || ((out_flags & TDM_OUT_BITS) && !bits)) {
+    if (out_flags & ~(TDM_OUT_SYMBOLS | TDM_OUT_DIBITS | TDM_OUT_BITS | TDM_OUT_PACKED)) { return fail(TDM_ERR_ARG, "tdm_process: unknown bits in out_flags"); }
+    if (((out_flags & TDM_OUT_SYMBOLS) && !syms) || ((out_flags & TDM_OUT_DIBITS) && !dibits) || ((out_flags & TDM_OUT_BITS) && !bits) ||
+        ((out_flags & TDM_OUT_PACKED) && !packed)) {
         return fail(TDM_ERR_ARG, "tdm_process: an output selected in out_flags has a null buffer");
     }
     const long long need = max_symbols_for(h->design, count);
     if ((out_flags & (TDM_OUT_SYMBOLS | TDM_OUT_DIBITS | TDM_OUT_BITS)) && out_stride < need) {
         return fail(TDM_ERR_ARG, "tdm_process: out_stride %lld < tdm_max_symbols(count) = %lld", (long long)out_stride, need);
+    }
+    if ((out_flags & TDM_OUT_PACKED) && packed_stride < need / 4) {
+        return fail(TDM_ERR_ARG, "tdm_process: packed_stride %lld < tdm_max_symbols(count) / 4 = %lld", (long long)packed_stride, need / 4);
     }
     DeviceGuard guard(h->device);
     const size_t C = (size_t)h->n_channels;
@@ -249,7 +277,10 @@ int tdm_process(tdm_handle* h, const float* iq, int64_t in_stride, int32_t count
         p.syms = (out_flags & TDM_OUT_SYMBOLS) ? reinterpret_cast<float2*>(syms) : nullptr;
         p.dibits = (out_flags & TDM_OUT_DIBITS) ? dibits : nullptr;
         p.bits = (out_flags & TDM_OUT_BITS) ? bits : nullptr;
-        p.out_stride = out_stride;
+        p.packed = (out_flags & TDM_OUT_PACKED) ? packed : nullptr;
+        p.packed_stride = packed_stride;
+        // only the packed output selected: rows are limited by what a call of `count` samples can emit
+        p.out_stride = (out_flags & (TDM_OUT_SYMBOLS | TDM_OUT_DIBITS | TDM_OUT_BITS)) ? out_stride : need;
         p.out_counts = out_counts;
         p.accumulate = 0;
         TDM_CUDA(cudaEventRecord(h->ev_start, h->stream));
@@ -264,10 +295,12 @@ int tdm_process(tdm_handle* h, const float* iq, int64_t in_stride, int32_t count
 
     int rc = ensure_staging(h, out_flags);
     if (rc != TDM_OK) { return rc; }
-    const long long dstride = h->max_syms;      // staging rows are max_syms wide
+    const long long dstride = h->max_syms;      // staging rows are max_syms wide (a multiple of 16)
     p.syms = (out_flags & TDM_OUT_SYMBOLS) ? h->d_syms : nullptr;
     p.dibits = (out_flags & TDM_OUT_DIBITS) ? h->d_dibits : nullptr;
     p.bits = (out_flags & TDM_OUT_BITS) ? h->d_bits : nullptr;
+    p.packed = (out_flags & TDM_OUT_PACKED) ? h->d_packed : nullptr;
+    p.packed_stride = dstride / 4;
     p.out_stride = dstride;
     p.out_counts = h->d_counts;
     p.in_stride = count;
@@ -317,6 +350,9 @@ int tdm_process(tdm_handle* h, const float* iq, int64_t in_stride, int32_t count
     }
     if (out_flags & TDM_OUT_BITS) {
         TDM_CUDA(cudaMemcpy2DAsync(bits, 2 * (size_t)out_stride, h->d_bits, 2 * (size_t)dstride, 2 * w, C, cudaMemcpyDeviceToHost, h->stream));
+    }
+    if (out_flags & TDM_OUT_PACKED) {
+        TDM_CUDA(cudaMemcpy2DAsync(packed, (size_t)packed_stride, h->d_packed, (size_t)(dstride / 4), w / 4, C, cudaMemcpyDeviceToHost, h->stream));
     }
     TDM_CUDA(cudaMemcpyAsync(out_counts, h->d_counts, sizeof(int) * C, cudaMemcpyDeviceToHost, h->stream));
     TDM_CUDA(cudaStreamSynchronize(h->stream));
@@ -633,8 +669,8 @@ int tdm_set_config(tdm_handle* h, const tdm_config* cfg) {
     h->design = d;
     h->max_syms = max_symbols_for(d, h->max_chunk);
     // staging sized from the old design may be too small now: drop it, it is re-made lazily
-    cudaFree(h->d_syms); cudaFree(h->d_dibits); cudaFree(h->d_bits);
-    h->d_syms = nullptr; h->d_dibits = nullptr; h->d_bits = nullptr;
+    cudaFree(h->d_syms); cudaFree(h->d_dibits); cudaFree(h->d_bits); cudaFree(h->d_packed);
+    h->d_syms = nullptr; h->d_dibits = nullptr; h->d_bits = nullptr; h->d_packed = nullptr;
     return upload_design(h);
 }
 
@@ -645,7 +681,7 @@ int tdm_get_design(const tdm_handle* h, tdm_design* out) {
 }
 
 int tdm_set_kernel_variant(tdm_handle* h, int32_t variant) {
-    if (!h || variant < 0) { return fail(TDM_ERR_ARG, "tdm_set_kernel_variant: bad arguments"); }
+    if (!h || variant < 0 || variant > tdm::kDemodVariants) { return fail(TDM_ERR_ARG, "tdm_set_kernel_variant: variant must be 0 (auto) .. %d", tdm::kDemodVariants); }
     h->variant = variant;
     return TDM_OK;
 }
@@ -667,6 +703,19 @@ int tdm_pack_dibits(tdm_handle* h, const uint8_t* dibits, int64_t in_stride, con
     DeviceGuard guard(h->device);
     const int n = tdm::launch_pack_dibits(dibits, in_stride, counts, packed, out_stride, h->n_channels, in_stride, h->stream);
     if (n < 0) { return fail(TDM_ERR_CUDA, "pack kernel launch failed"); }
+    h->launches += n;
+    return TDM_OK;
+}
+
+int tdm_unpack_dibits(tdm_handle* h, const uint8_t* packed, int64_t in_stride, const int32_t* counts, int32_t n_rows,
+                      uint8_t* dibits, int64_t dibit_stride, uint8_t* bits, int64_t bit_stride, int64_t max_symbols) {
+    if (!h || !packed || !counts || (!dibits && !bits) || n_rows <= 0 || max_symbols < 0) { return fail(TDM_ERR_ARG, "tdm_unpack_dibits: bad arguments"); }
+    if (in_stride * 4 < max_symbols || (dibits && dibit_stride < max_symbols) || (bits && bit_stride < 2 * max_symbols)) {
+        return fail(TDM_ERR_ARG, "tdm_unpack_dibits: a row stride is smaller than max_symbols needs");
+    }
+    DeviceGuard guard(h->device);
+    const int n = tdm::launch_unpack_dibits(packed, in_stride, counts, dibits, dibit_stride, bits, bit_stride, n_rows, max_symbols, h->stream);
+    if (n < 0) { return fail(TDM_ERR_CUDA, "unpack kernel launch failed"); }
     h->launches += n;
     return TDM_OK;
 }

@@ -126,8 +126,22 @@ extern "C" int tdm_design_from_config(const tdm_config* cfg, tdm_design* d) {
     const int nt = cfg->rrc_tap_count;
     if (nt < 1 || nt > TDM_MAX_TAPS) { return TDM_ERR_UNSUPPORTED; }
     if (!(cfg->samplerate > 0) || !(cfg->symbolrate > 0) || !(cfg->rrc_beta > 0)) { return TDM_ERR_ARG; }
+    if (!std::isfinite(cfg->samplerate) || !std::isfinite(cfg->symbolrate) || !std::isfinite(cfg->rrc_beta) || !std::isfinite(cfg->agc_rate) ||
+        !std::isfinite(cfg->costas_bandwidth) || !std::isfinite(cfg->fll_bandwidth) || !std::isfinite(cfg->omega_gain) ||
+        !std::isfinite(cfg->mu_gain) || !std::isfinite(cfg->omega_rel_limit)) { return TDM_ERR_ARG; }
+    if (!(cfg->omega_rel_limit >= 0.0) || !(cfg->omega_rel_limit < 1.0)) { return TDM_ERR_ARG; }
+    if (cfg->flags & ~TDM_CFG_FASTAMP_RE_ONLY) { return TDM_ERR_ARG; }
+    // The kernels emit at most 8 symbols per 8-sample tick into 16-entry hand-over rings and size the output rows from
+    // the smallest possible advance per symbol, omega_min - |mu_gain| (complex_fd.cpp:140-143: mu += omega + muGain*e,
+    // |e| <= 1, advance = floor(mu)): below ~1.25 samples per symbol both would have to change.  The reference itself
+    // runs at 2 samples per symbol (src/main.cpp:35,84).
+    {
+        const double omega_min = cfg->samplerate / cfg->symbolrate * (1.0 - cfg->omega_rel_limit);
+        if (!(omega_min - std::fabs(cfg->mu_gain) >= 1.25)) { return TDM_ERR_UNSUPPORTED; }
+    }
     std::memset(d, 0, sizeof(*d));
     d->ntaps = nt;
+    d->fastamp_re_only = (cfg->flags & TDM_CFG_FASTAMP_RE_ONLY) ? 1 : 0;
     // A filter shorter than the kernels' 65 taps is zero-padded at the OLD end: fma(0, x, acc)
     // leaves acc untouched, so the padded filter is bit-identical to the short one.
     const int pad = TDM_MAX_TAPS - nt;

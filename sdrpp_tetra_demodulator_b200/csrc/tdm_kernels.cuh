@@ -35,19 +35,28 @@ struct DemodParams {
     float2* syms;                   // [C][out_stride] or nullptr
     uint8_t* dibits;                // [C][out_stride] or nullptr
     uint8_t* bits;                  // [C][2*out_stride] or nullptr
+    uint8_t* packed;                // [C][packed_stride] or nullptr: 4 dibits per byte, first symbol in bits 7..6
     long long out_stride;
+    long long packed_stride;
+    int fastamp_re_only;            // tdm_design::fastamp_re_only (selects the kernel instantiation)
     int* out_counts;                // [C]
     int accumulate;                 // 0: rows are written from symbol 0 and out_counts is overwritten;
                                     // 1: append after the out_counts[c] symbols already there (time slices of one call)
     tdm_channel_state* states;      // [C]
+    int debug_mask;                 // development builds only (-DTDM_ABLATE): bit r set = role r of the ws4 pipeline skips its work
 };
 
 // variant: 0 = auto.  Returns the number of kernels launched, or <0 on launch error.
+constexpr int kDemodVariants = 11;      // valid explicit variants are 1..kDemodVariants
 int launch_demod(const DemodParams& p, int variant, cudaStream_t stream);
 const char* demod_variant_name(int variant);
 
 int launch_pack_dibits(const uint8_t* dibits, long long in_stride, const int* counts, uint8_t* packed,
                        long long out_stride, int n_channels, long long max_syms, cudaStream_t stream);
+
+// packed rows (4 dibits per byte) -> one dibit per byte and/or one bit per byte (either may be null)
+int launch_unpack_dibits(const uint8_t* packed, long long in_stride, const int* counts, uint8_t* dibits, long long dibit_stride,
+                         uint8_t* bits, long long bit_stride, int n_channels, long long max_syms, cudaStream_t stream);
 
 int launch_synth(const tdm_synth_params& sp, int n_channels, long long n_samples, long long stride,
                  int first_channel, float2* iq, uint8_t* tx_dibits, long long tx_stride, cudaStream_t stream);

@@ -37,6 +37,7 @@ class DemodResult:
     symbols: object | None  # [C][S][2] float32
     dibits: object | None   # [C][S] uint8, values 0..3
     bits: object | None     # [C][2S] uint8, values 0/1
+    packed: object | None = None   # [C][S/4] uint8, four dibits per byte, first symbol in bits 7..6 (TDM_OUT_PACKED)
 
 
 class Demodulator:
@@ -129,12 +130,12 @@ class Demodulator:
         return int(self._lib.tdm_launch_count(self._h))
 
     # -- the hot call
-    def process(self, iq, symbols: bool = False, dibits: bool = True, bits: bool = False,
+    def process(self, iq, symbols: bool = False, dibits: bool = True, bits: bool = False, packed: bool = False,
                 out: DemodResult | None = None) -> DemodResult:
         """iq: [C][N][2] float32 -- a CUDA torch tensor (zero-copy, asynchronous on the handle's stream)
         or a numpy array (staged through the library, synchronous)."""
         flags = (capi.TDM_OUT_SYMBOLS if symbols else 0) | (capi.TDM_OUT_DIBITS if dibits else 0) | \
-                (capi.TDM_OUT_BITS if bits else 0)
+                (capi.TDM_OUT_BITS if bits else 0) | (capi.TDM_OUT_PACKED if packed else 0)
         if isinstance(iq, np.ndarray):
             return self._process_host(iq, flags)
         return self._process_device(iq, flags, out)
@@ -148,11 +149,12 @@ class Demodulator:
         syms = np.zeros((self.n_channels, s, 2), np.float32) if flags & capi.TDM_OUT_SYMBOLS else None
         dib = np.zeros((self.n_channels, s), np.uint8) if flags & capi.TDM_OUT_DIBITS else None
         bit = np.zeros((self.n_channels, 2 * s), np.uint8) if flags & capi.TDM_OUT_BITS else None
+        pk = np.zeros((self.n_channels, s // 4), np.uint8) if flags & capi.TDM_OUT_PACKED else None
         counts = np.zeros(self.n_channels, np.int32)
-        p = lambda a: None if a is None else a.ctypes.data_as(C.c_void_p)
-        capi.check(self._lib.tdm_process(self._h, p(iq), n, n, p(syms), p(dib), p(bit), s, p(counts), flags,
-                                         capi.TDM_MEM_HOST), "tdm_process")
-        return DemodResult(counts, syms, dib, bit)
+        p = lambda a: None if a is None else a.ctypes.data
+        io = capi.TdmIo(p(iq), n, n, capi.TDM_MEM_HOST, p(syms), p(dib), p(bit), p(pk), s, s // 4, p(counts), flags, 0)
+        capi.check(self._lib.tdm_process_io(self._h, C.byref(io)), "tdm_process_io")
+        return DemodResult(counts, syms, dib, bit, pk)
 
     def _process_device(self, iq, flags: int, out: DemodResult | None) -> DemodResult:
         torch = _torch()
@@ -171,7 +173,8 @@ class Demodulator:
                 torch.empty(self.n_channels, dtype=torch.int32, device=dev),
                 torch.empty((self.n_channels, s, 2), dtype=torch.float32, device=dev) if flags & capi.TDM_OUT_SYMBOLS else None,
                 torch.empty((self.n_channels, s), dtype=torch.uint8, device=dev) if flags & capi.TDM_OUT_DIBITS else None,
-                torch.empty((self.n_channels, 2 * s), dtype=torch.uint8, device=dev) if flags & capi.TDM_OUT_BITS else None)
+                torch.empty((self.n_channels, 2 * s), dtype=torch.uint8, device=dev) if flags & capi.TDM_OUT_BITS else None,
+                torch.empty((self.n_channels, s // 4), dtype=torch.uint8, device=dev) if flags & capi.TDM_OUT_PACKED else None)
         stride = None
         for t, div in ((out.symbols, 1), (out.dibits, 1), (out.bits, 2)):
             if t is not None:
@@ -179,9 +182,10 @@ class Demodulator:
                 stride = st if stride is None else min(stride, st)
         if stride is None:
             stride = s
-        p = lambda t: C.c_void_p(0 if t is None else t.data_ptr())
-        capi.check(self._lib.tdm_process(self._h, p(iq), in_stride, n, p(out.symbols), p(out.dibits), p(out.bits),
-                                         stride, p(out.counts), flags, capi.TDM_MEM_DEVICE), "tdm_process")
+        p = lambda t: None if t is None else t.data_ptr()
+        io = capi.TdmIo(p(iq), in_stride, n, capi.TDM_MEM_DEVICE, p(out.symbols), p(out.dibits), p(out.bits), p(out.packed),
+                        stride, 0 if out.packed is None else out.packed.shape[1], p(out.counts), flags, 0)
+        capi.check(self._lib.tdm_process_io(self._h, C.byref(io)), "tdm_process_io")
         return out
 
     def process_long(self, iq, warmup: int = 65536, out=None):
@@ -242,6 +246,22 @@ class Demodulator:
         capi.check(self._lib.tdm_pack_dibits(self._h, C.c_void_p(dibits.data_ptr()), s, C.c_void_p(counts.data_ptr()),
                                              C.c_void_p(packed.data_ptr()), packed.shape[1]), "tdm_pack_dibits")
         return packed
+
+
+    def unpack_dibits(self, packed, counts, max_symbols: int | None = None, dibits: bool = True, bits: bool = False):
+        """Packed rows (this handle's, or the rows gathered from every rank: any row count) -> one dibit per byte
+        and / or one bit per byte, the stream BitUnpacker / the NETSYMS sink emit (tdm_unpack_dibits)."""
+        torch = _torch()
+        rows = int(packed.shape[0])
+        m = int(packed.shape[1]) * 4 if max_symbols is None else int(max_symbols)
+        m16 = (m + 15) // 16 * 16
+        self.set_stream(torch.cuda.current_stream(packed.device).cuda_stream)
+        d = torch.empty((rows, m16), dtype=torch.uint8, device=packed.device) if dibits else None
+        b = torch.empty((rows, 2 * m16), dtype=torch.uint8, device=packed.device) if bits else None
+        p = lambda t: C.c_void_p(0 if t is None else t.data_ptr())
+        capi.check(self._lib.tdm_unpack_dibits(self._h, p(packed), packed.stride(0), p(counts), rows, p(d), m16, p(b), 2 * m16, m),
+                   "tdm_unpack_dibits")
+        return d, b
 
 
 def synth_capture(n_channels: int, n_samples: int, device: int = 0, snr_db: float = 30.0,

@@ -34,6 +34,7 @@ class GoldenCase:
         self.n_samples = int(z["n_samples"])
         self.snr_db = float(z["snr_db"])
         self.first_channel = int(z["first_channel"])
+        self.fastamp_re_only = bool(int(z["fastamp_re_only"])) if "fastamp_re_only" in z else False
         self.counts = z["counts"]
         self.dibits = [unpack2(z[f"dibits_packed_{c}"], int(self.counts[c])) for c in range(self.n_channels)]
         self.ill = [np.unpackbits(z[f"ill_packed_{c}"])[:int(self.counts[c])].astype(bool)

@@ -30,12 +30,13 @@ def pack2(d):
     return (p[:, 0] << 6 | p[:, 1] << 4 | p[:, 2] << 2 | p[:, 3]).astype(np.uint8)
 
 
-def make_case(name, n_channels, n_samples, snr_db, first_channel=0, store_input=False, store_syms=False):
+def make_case(name, n_channels, n_samples, snr_db, first_channel=0, store_input=False, store_syms=False, re_only=False):
     sp = O.default_sg_params(snr_db=snr_db)
     iq = O.generate(n_channels, n_samples, sp, first_channel=first_channel)
-    a = O.OracleA(n_channels)
+    a = O.OracleA(n_channels, fastamp_re_only=re_only)
     counts, syms, dibits, _ = a.process(iq, want_syms=True)
     out = {
+        "fastamp_re_only": int(re_only),
         "n_channels": n_channels, "n_samples": n_samples, "snr_db": snr_db, "first_channel": first_channel,
         "input_sha256": np.frombuffer(hashlib.sha256(iq.tobytes()).digest(), np.uint8),
         "counts": counts,
@@ -91,3 +92,8 @@ if __name__ == "__main__":
     make_case("batch_c4_n60000_snr20", 4, 60_000, 20.0, first_channel=100)
     # a small case that carries its own input and the reference's symbols
     make_case("small_c2_n4096", 2, 4096, 30.0, store_input=True, store_syms=True)
+    # the same captures through the reference built with the OTHER reading of complex_t::fastAmplitude()
+    # (oracle/_ref/libtetra_ref_reonly.so; tdm_config.flags & TDM_CFG_FASTAMP_RE_ONLY on the product side)
+    make_case("cfg1_c1_n1e6_snr30_reonly", 1, 1_000_000, 30.0, re_only=True)
+    make_case("batch_c8_n60000_snr30_reonly", 8, 60_000, 30.0, re_only=True)
+    make_case("batch_c4_n60000_snr20_reonly", 4, 60_000, 20.0, first_channel=100, re_only=True)

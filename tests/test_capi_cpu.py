@@ -23,7 +23,7 @@ def test_library_exports_every_declared_symbol(pkg):
     for name in declared:
         assert hasattr(L, name), f"{name} is declared in include/tdm_b200.h but not exported"
     assert set(declared) == set(pkg.capi.EXPORTED_SYMBOLS)
-    assert L.tdm_abi_version() == 1
+    assert L.tdm_abi_version() == 2
     burst = _header_functions("tdm_burst_b200.h")
     assert set(burst) == set(pkg.capi.EXPORTED_BURST_SYMBOLS), set(burst) ^ set(pkg.capi.EXPORTED_BURST_SYMBOLS)
     for name in burst:

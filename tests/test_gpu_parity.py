@@ -17,7 +17,7 @@ from conftest import golden_case, require_golden_input
 
 pytestmark = pytest.mark.gpu
 
-VARIANTS = [1, 2, 3, 4, 5, 6, 7, 8, 9]
+VARIANTS = [1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11]     # tpc4, tpc8, tpc4x4, ws4 placements 0..3 at one and two CTAs per SM
 
 
 @pytest.fixture(scope="module")
@@ -71,14 +71,23 @@ def test_bit_exact_vs_oracle_b(O, pkg, torch_cuda, variant, n_channels, n_sample
         assert_matches_oracle_b(O, dm, ob, res, cb, sb, db, bb)
 
 
-@pytest.mark.parametrize("name", ["small_c2_n4096", "batch_c8_n60000_snr30", "batch_c4_n60000_snr20", "cfg1_c1_n1e6_snr30"])
+def _config_for(pkg, g):
+    cfg = pkg.default_config()
+    if g.fastamp_re_only:
+        cfg.flags |= pkg.capi.TDM_CFG_FASTAMP_RE_ONLY
+    return cfg
+
+
+@pytest.mark.parametrize("name", ["small_c2_n4096", "batch_c8_n60000_snr30", "batch_c4_n60000_snr20", "cfg1_c1_n1e6_snr30",
+                                  "batch_c8_n60000_snr30_reonly", "batch_c4_n60000_snr20_reonly", "cfg1_c1_n1e6_snr30_reonly"])
 def test_bits_vs_reference_golden(O, pkg, torch_cuda, name):
     """BASELINE.json configs[0] (1 channel x 1e6 samples) and the batch fixtures: the CUDA path against the
-    reference's own decoded bits."""
+    reference's own decoded bits -- for both readings of complex_t::fastAmplitude() (the *_reonly fixtures were
+    written by the reference compiled with the other reading, the product runs with TDM_CFG_FASTAMP_RE_ONLY)."""
     torch = torch_cuda
     g = golden_case(name)
     require_golden_input(g)
-    with pkg.Demodulator(g.n_channels, g.n_samples) as dm:
+    with pkg.Demodulator(g.n_channels, g.n_samples, config=_config_for(pkg, g)) as dm:
         res = dm.process(torch.from_numpy(g.iq).cuda(), dibits=True)
         torch.cuda.synchronize()
         counts = res.counts.cpu().numpy()
@@ -114,7 +123,7 @@ def test_live_reference_when_present(O, pkg, torch_cuda):
     a.close()
 
 
-@pytest.mark.parametrize("variant", [0, 4, 5, 7])
+@pytest.mark.parametrize("variant", [0, 2, 5, 8])
 @pytest.mark.parametrize("chunk", [32768, 4097, 7])
 def test_chunk_invariance_and_streaming_state(O, pkg, torch_cuda, chunk, variant):
     """BASELINE.json configs[4] in miniature: state carried across launches; any chunking gives the
@@ -244,7 +253,7 @@ def test_set_config_short_filter(O, pkg, torch_cuda):
         assert_matches_oracle_b(O, dm, ob, res, cb, sb, db)
 
 
-@pytest.mark.parametrize("variant", [2, 4, 5, 7])
+@pytest.mark.parametrize("variant", [2, 4, 8])
 def test_extreme_amplitudes(O, pkg, torch_cuda, variant):
     """AGC square root on its rare inputs -- exact zeros, denormal-scale and huge samples -- must stay the
     IEEE-correct sqrtf the CPU computes (the kernel uses a branch-free MUFU.RSQ + FMA refinement)."""
@@ -261,6 +270,98 @@ def test_extreme_amplitudes(O, pkg, torch_cuda, variant):
         dm.set_kernel_variant(variant)
         res = dm.process(torch.from_numpy(iq).cuda(), symbols=True, dibits=True)
         assert_matches_oracle_b(O, dm, ob, res, cb, sb, db)
+
+
+@pytest.mark.parametrize("variant", [2, 4, 9])
+def test_fll_frequency_jumps_take_the_exact_path(O, pkg, torch_cuda, variant):
+    """The FLL's NCO is evaluated from a range reduction prepared one sample ahead; when the loop frequency jumps (a
+    burst arriving while the AGC gain is wide open bangs it between its clamps) the prepared reduction is unusable
+    and the exact per-sample rule falls back to the classic one.  The warp-specialised kernel speculates per tick
+    and replays: force that path hard, in some lanes only, at every position within a tick."""
+    torch = torch_cuda
+    C_, N = 37, 9000
+    iq = O.generate(C_, N)
+    rng = np.random.default_rng(5)
+    for c in range(0, C_, 3):
+        for k in range(6):
+            n0 = int(rng.integers(200, N - 400)) + k           # every residue mod 8
+            iq[c, n0:n0 + int(rng.integers(1, 40))] *= float(rng.uniform(3, 12))    # (FastAGC itself diverges beyond |x g| ~ 100)
+        iq[c, 3000:3400] = 0.0                                  # silence: the gain runs away, then the signal returns
+    # With the plugin's loop bandwidth the frequency moves by ~1e-4 rad per sample and the fallback never fires on a
+    # sane signal; a wide loop (setFllBandwidth, src/dsp/pi4dqpsk.h:59) moves it by up to ~0.1 rad per sample.
+    n_fallback = 0
+    for re_only, bw in ((False, 0.006), (False, 0.25), (True, 0.25)):
+        cfg_o = O.OracleB.default_config()
+        cfg_o.fll_bandwidth = bw
+        ob = O.OracleB(C_, cfg_o, fastamp_re_only=re_only)
+        cb, sb, db, _ = ob.process(iq)
+        assert np.isfinite(sb).all()
+        cfg = pkg.default_config()
+        cfg.fll_bandwidth = bw
+        cfg.flags = pkg.capi.TDM_CFG_FASTAMP_RE_ONLY if re_only else 0
+        with pkg.Demodulator(C_, N, config=cfg) as dm:
+            dm.set_kernel_variant(variant)
+            res = dm.process(torch.from_numpy(iq).cuda(), symbols=True, dibits=True)
+            torch.cuda.synchronize()
+            st = dm.get_state()
+            for f in ("fll_phase", "fll_freq", "fll_r", "fll_quad", "agc_gain", "x_hist"):
+                a, b = st[f], ob.states[f]
+                assert np.array_equal(a.view(np.uint32), b.view(np.uint32)), (f, bw, re_only)
+            counts = res.counts.cpu().numpy()
+            assert np.array_equal(counts, cb)
+            dib, sym = res.dibits.cpu().numpy(), res.symbols.cpu().numpy()
+            for c in range(C_):
+                assert np.array_equal(dib[c, :cb[c]], db[c, :cb[c]]), c
+                assert np.array_equal(_u32(sym[c, :cb[c]]), _u32(sb[c, :cb[c]])), c
+        if bw > 0.1:
+            n_fallback += int(O.count_fll_fallbacks(iq, cfg_o, re_only))
+    assert n_fallback > 100, "the capture did not exercise the fallback"
+
+
+@pytest.mark.parametrize("variant", [2, 4, 8])
+def test_packed_output_is_the_dibit_stream(O, pkg, torch_cuda, variant):
+    """TDM_OUT_PACKED (what the multi-GPU gather ships) is written by the slicer itself: it must equal the dibit
+    stream 4 per byte, through any chunking (bytes straddle calls) and through the time-sliced host path; and
+    tdm_unpack_dibits must give back DQPSKSymbolExtractor's and BitUnpacker's streams (src/dsp/bit_unpacker.cpp:4-10)."""
+    torch = torch_cuda
+    from sdrpp_tetra_demodulator_b200.sharding import unpack_dibits
+    C_, N = 35, 40003
+    iq = O.generate(C_, N)
+    dev = torch.from_numpy(iq).cuda()
+    with pkg.Demodulator(C_, N) as dm:
+        dm.set_kernel_variant(variant)
+        r = dm.process(dev, dibits=True, bits=True, packed=True)
+        torch.cuda.synchronize()
+        counts, dib, pk, bits = r.counts.cpu().numpy(), r.dibits.cpu().numpy(), r.packed.cpu().numpy(), r.bits.cpu().numpy()
+        for c in range(C_):
+            n = int(counts[c])
+            assert np.array_equal(unpack_dibits(pk[c], n), dib[c, :n]), c
+            if n % 4:
+                assert pk[c, n // 4] & ((1 << (2 * (4 - n % 4))) - 1) == 0          # zero padded
+        only = dm.process(dev[:, :0].contiguous(), packed=True, dibits=False)           # empty call: nothing written, counts 0
+        torch.cuda.synchronize()
+        assert not only.counts.cpu().numpy().any()
+        d2, b2 = dm.unpack_dibits(r.packed, r.counts, max_symbols=int(counts.max()), dibits=True, bits=True)
+        torch.cuda.synchronize()
+        d2, b2 = d2.cpu().numpy(), b2.cpu().numpy()
+        for c in range(C_):
+            n = int(counts[c])
+            assert np.array_equal(d2[c, :n], dib[c, :n]) and np.array_equal(b2[c, :2 * n], bits[c, :2 * n]), c
+    with pkg.Demodulator(C_, N) as dm:                      # host path: 8 time slices append to the packed rows mid-byte
+        dm.set_kernel_variant(variant)
+        rh = dm.process(iq, dibits=True, packed=True)
+        for c in range(C_):
+            n = int(rh.counts[c])
+            assert np.array_equal(rh.dibits[c, :n], dib[c, :n])
+            assert np.array_equal(unpack_dibits(rh.packed[c], n), dib[c, :n]), c
+    with pkg.Demodulator(C_, N) as dm:                      # packed only, device path
+        dm.set_kernel_variant(variant)
+        rp = dm.process(dev, dibits=False, packed=True)
+        torch.cuda.synchronize()
+        assert np.array_equal(rp.counts.cpu().numpy(), counts)
+        pk2 = rp.packed.cpu().numpy()
+        for c in range(C_):
+            assert np.array_equal(pk2[c, :(counts[c] + 3) // 4], pk[c, :(counts[c] + 3) // 4]), c
 
 
 def test_empty_and_tiny_calls(O, pkg, torch_cuda):

@@ -7,7 +7,8 @@ import pytest
 
 from conftest import golden_case, require_golden_input
 
-GOLDEN_CASES = ["small_c2_n4096", "batch_c8_n60000_snr30", "batch_c4_n60000_snr20", "cfg1_c1_n1e6_snr30"]
+GOLDEN_CASES = ["small_c2_n4096", "batch_c8_n60000_snr30", "batch_c4_n60000_snr20", "cfg1_c1_n1e6_snr30",
+                "batch_c8_n60000_snr30_reonly", "batch_c4_n60000_snr20_reonly", "cfg1_c1_n1e6_snr30_reonly"]
 
 
 def test_state_struct_sizes(O, pkg):
@@ -84,12 +85,48 @@ def test_canonical_sincos_accuracy(O):
     assert worst < 2.5e-7, worst
 
 
+def test_canonical_fll_nco_accuracy(O):
+    """The FLL's NCO (range reduction prepared one sample ahead, oracle_b.c ob_fll_*) must stay a faithful stand-in
+    for math::phasor's cosf/sinf of the wrapped loop phase (src/dsp/fll.cpp:137) for EVERY state the loop can be
+    in: any phase, any frequency within the +-pi/2 clamp, any jump of the frequency (fallback path)."""
+    L = O.lib_b()
+    rng = np.random.default_rng(11)
+    s, c = C.c_float(), C.c_float()
+    worst_near, worst_far, worst_small_f = 0.0, 0.0, 0.0
+    n0 = L.ob_fll_fallback_count()
+    pi_f = np.float32(3.1415926535)
+    two_pi = np.float32(pi_f - (-pi_f))
+    for i in range(60000):
+        phi = np.float32(rng.uniform(-pi_f, pi_f))
+        f_old = np.float32(rng.uniform(-1.5707, 1.5707) if i % 3 else rng.normal(0, 0.05))
+        jump = [1e-4, 1e-2, 0.5][i % 3]
+        f_new = np.float32(np.clip(f_old + rng.normal(0, jump), -1.5707963, 1.5707963))
+        L.ob_fll_nco(float(phi), float(f_old), float(f_new), C.byref(s), C.byref(c))
+        # two equally legitimate targets: the phase as the reference holds it (float sum, wrapped by the float 2 pi:
+        # what the classic fall-back path evaluates), and the unrounded sum (what the prepared reduction evaluates:
+        # it never rounds phi + f, and a wrap costs it nothing).  They differ by up to 3e-7 rad themselves.
+        ph = np.float32(phi + f_new)
+        ph = np.float32(ph - two_pi) if ph > pi_f else (np.float32(ph + two_pi) if ph < -pi_f else ph)
+        ex = np.float64(phi) + np.float64(f_new)
+        e_ref = max(abs(s.value - np.sin(np.float64(ph))), abs(c.value - np.cos(np.float64(ph))))
+        e_ex = max(abs(s.value - np.sin(ex)), abs(c.value - np.cos(ex)))
+        worst_near = max(worst_near, min(e_ref, e_ex))
+        worst_far = max(worst_far, max(e_ref, e_ex))
+        if abs(f_old) < 0.3 and abs(f_new) < 0.3:       # +-1.7 kHz at 36 kS/s: where a locked loop lives
+            worst_small_f = max(worst_small_f, min(e_ref, e_ex))
+    # r = r0 + f cancels two numbers of size |f| + pi/4: half an ulp of that is the price of the short recurrence
+    assert worst_small_f < 1.2e-7, worst_small_f
+    assert worst_near < 2.5e-7, worst_near
+    assert worst_far < 6.5e-7, worst_far
+    assert L.ob_fll_fallback_count() - n0 > 3000       # the big jumps went through the classic reduction
+
+
 @pytest.mark.parametrize("name", GOLDEN_CASES)
 def test_oracle_b_bits_equal_reference_golden(O, name):
     """Decoded dibits of the canonical-order restatement == the reference's own chain (fixture from Oracle A)."""
     g = golden_case(name)
     require_golden_input(g)
-    b = O.OracleB(g.n_channels)
+    b = O.OracleB(g.n_channels, fastamp_re_only=g.fastamp_re_only)
     counts, syms, dibits, _ = b.process(g.iq, nthreads=4)
     for c in range(g.n_channels):
         g.assert_dibits_match(c, dibits[c], counts[c])
@@ -100,14 +137,14 @@ def test_oracle_b_bits_equal_reference_golden(O, name):
         assert err < 0.15   # float trajectories are NOT expected to match the reference's (chaotic at 1 ulp)
 
 
-@pytest.mark.parametrize("name", GOLDEN_CASES[:3])
+@pytest.mark.parametrize("name", GOLDEN_CASES[:3] + GOLDEN_CASES[4:6])
 def test_live_reference_reproduces_golden(O, name):
     """Where oracle/_ref exists, it must reproduce the committed fixture exactly (the fixture is its output)."""
-    if not O.have_ref():
-        pytest.skip("oracle/_ref not built here")
     g = golden_case(name)
+    if not O.have_ref(g.fastamp_re_only):
+        pytest.skip("oracle/_ref not built here")
     require_golden_input(g)
-    a = O.OracleA(g.n_channels)
+    a = O.OracleA(g.n_channels, fastamp_re_only=g.fastamp_re_only)
     counts, _, dibits, bits = a.process(g.iq, want_syms=False, want_bits=True)
     assert np.array_equal(counts, g.counts)
     for c in range(g.n_channels):
