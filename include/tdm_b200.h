@@ -282,10 +282,34 @@ int tdm_pack_dibits(tdm_handle* h, const uint8_t* dibits, int64_t in_stride, con
 int tdm_unpack_dibits(tdm_handle* h, const uint8_t* packed, int64_t in_stride, const int32_t* counts, int32_t n_rows,
                       uint8_t* dibits, int64_t dibit_stride, uint8_t* bits, int64_t bit_stride, int64_t max_symbols);
 
+/* ---- multi-GPU epilogue: gather of the decoded symbol streams over NCCL (BASELINE.json configs[3]) ----
+ * Channels are sharded by contiguous, equal-sized channel blocks, one handle per GPU; nothing is exchanged while
+ * demodulating.  Each rank's TDM_OUT_PACKED rows + symbol counts are gathered to rank `dst`, rank-major (= channel-
+ * major).  NCCL (libnccl.so.2, 2.x) is loaded at run time; without it these four calls return TDM_ERR_UNSUPPORTED
+ * and everything else works.  The reference has no counterpart: it runs one plugin instance per channel in one
+ * process (src/main.cpp:51) and its only network output is the UDP symbol sink (src/main.cpp:174,385-389), which
+ * rank `dst` can feed after tdm_unpack_dibits.
+ *   tdm_comm_unique_id : rank 0 makes the 128-byte id (ncclGetUniqueId) and ships it to the other ranks by any means
+ *   tdm_comm_create    : ncclCommInitRank on `device` (collective: every rank calls it)
+ *   tdm_comm_adopt     : wrap an ncclComm_t the host application already has (not destroyed by tdm_comm_destroy)
+ *   tdm_gather_packed  : packed [n_rows][packed_stride] + counts [n_rows] of every rank -> packed_all
+ *                        [world * n_rows][packed_stride], counts_all [world * n_rows] on rank dst (NULL elsewhere);
+ *                        device pointers, asynchronous on cuda_stream (a cudaStream_t; give a stream other than the
+ *                        handle's to overlap the gather of one call with the demodulation of the next). */
+#define TDM_COMM_ID_BYTES 128
+typedef struct tdm_comm tdm_comm;
+int tdm_comm_unique_id(uint8_t id[TDM_COMM_ID_BYTES]);
+int tdm_comm_create(const uint8_t id[TDM_COMM_ID_BYTES], int32_t rank, int32_t world, int32_t device, tdm_comm** out);
+int tdm_comm_adopt(void* nccl_comm, int32_t rank, int32_t world, int32_t device, tdm_comm** out);
+int tdm_comm_destroy(tdm_comm* c);
+int tdm_gather_packed(tdm_comm* c, int32_t dst, int32_t n_rows, const uint8_t* packed, int64_t packed_stride, const int32_t* counts,
+                      uint8_t* packed_all, int32_t* counts_all, void* cuda_stream);
+
 /* Deterministic synthetic TETRA-mapped pi/4-DQPSK capture, generated on the
  * device: channel c uses data seed seed_data+c and noise seed
  * seed_noise+c.  iq_dev: [C][stride] device floats pairs.  tx_dibits_dev
- * ([C][n/2+64] bytes, may be NULL) receives the transmitted dibits.
+ * ([C][n/2+64] bytes, may be NULL) receives the transmitted dibits; iq_dev may be
+ * NULL when only those are wanted.
  * Test/bench signal source; not part of the reference's surface. */
 typedef struct tdm_synth_params {
     double snr_db;          /* Es/N0 in dB                          */

@@ -43,6 +43,7 @@ EXPORTED_SYMBOLS = [
     "tdm_get_metrics", "tdm_set_config", "tdm_get_design", "tdm_set_kernel_variant", "tdm_last_kernel_ms",
     "tdm_launch_count", "tdm_pack_dibits", "tdm_synth_capture", "tdm_last_error", "tdm_abi_version",
     "tdm_process_long", "tdm_process_long_batch", "tdm_process_io", "tdm_unpack_dibits",
+    "tdm_comm_unique_id", "tdm_comm_create", "tdm_comm_adopt", "tdm_comm_destroy", "tdm_gather_packed",
 ]
 # ... and include/tdm_burst_b200.h
 EXPORTED_BURST_SYMBOLS = [
@@ -161,6 +162,11 @@ def lib() -> C.CDLL:
         "tdm_process": (C.c_int, [vp, vp, i64, i32, vp, vp, vp, i64, vp, u32, i32]),
         "tdm_process_io": (C.c_int, [vp, C.POINTER(TdmIo)]),
         "tdm_unpack_dibits": (C.c_int, [vp, vp, i64, vp, i32, vp, i64, vp, i64, i64]),
+        "tdm_comm_unique_id": (C.c_int, [vp]),
+        "tdm_comm_create": (C.c_int, [vp, i32, i32, i32, C.POINTER(vp)]),
+        "tdm_comm_adopt": (C.c_int, [vp, i32, i32, i32, C.POINTER(vp)]),
+        "tdm_comm_destroy": (C.c_int, [vp]),
+        "tdm_gather_packed": (C.c_int, [vp, i32, i32, vp, i64, vp, vp, vp, vp]),
         "tdm_reset": (C.c_int, [vp]),
         "tdm_reset_all": (C.c_int, [vp]),
         "tdm_get_state": (C.c_int, [vp, vp, i32]),

@@ -722,7 +722,7 @@ int tdm_unpack_dibits(tdm_handle* h, const uint8_t* packed, int64_t in_stride, c
 
 int tdm_synth_capture(int32_t device, void* cuda_stream, const tdm_synth_params* p, int32_t n_channels, int64_t n_samples,
                       int64_t stride, int32_t first_channel, float* iq_dev, uint8_t* tx_dibits_dev, int64_t tx_stride) {
-    if (!p || !iq_dev || n_channels <= 0 || n_samples <= 0 || stride < n_samples) { return fail(TDM_ERR_ARG, "tdm_synth_capture: bad arguments"); }
+    if (!p || (!iq_dev && !tx_dibits_dev) || n_channels <= 0 || n_samples <= 0 || (iq_dev && stride < n_samples)) { return fail(TDM_ERR_ARG, "tdm_synth_capture: bad arguments"); }
     DeviceGuard guard(device);
     const int n = tdm::launch_synth(*p, n_channels, n_samples, stride, first_channel, reinterpret_cast<float2*>(iq_dev),
                                     tx_dibits_dev, tx_stride, (cudaStream_t)cuda_stream);

@@ -89,7 +89,7 @@ __global__ void __launch_bounds__(256) synth_kernel(tdm_synth_params sp, int fir
     const float cs8x[8] = { 1.f, 0.70710678f, 0.f, -0.70710678f, -1.f, -0.70710678f, 0.f, 0.70710678f };
     float2* row = iq + (long long)cl * stride;
 
-    for (int i = threadIdx.x; i < kBlockSamples; i += blockDim.x) {
+    for (int i = threadIdx.x; iq != nullptr && i < kBlockSamples; i += blockDim.x) {
         const long long n = n0 + i;
         if (n >= n_samples) { break; }
         long long kmin = (n - (kSpan + 1) + 1) / 2;
@@ -142,7 +142,7 @@ int launch_synth(const tdm_synth_params& sp, int n_channels, long long n_samples
     for (int c0 = 0; c0 < n_channels; c0 += 32768) {
         const int nc = (n_channels - c0) < 32768 ? (n_channels - c0) : 32768;
         dim3 grid((unsigned)nblk, (unsigned)nc);
-        synth_kernel<<<grid, 256, 0, stream>>>(sp, first_channel + c0, n_samples, stride, iq + (long long)c0 * stride,
+        synth_kernel<<<grid, 256, 0, stream>>>(sp, first_channel + c0, n_samples, stride, iq ? iq + (long long)c0 * stride : nullptr,
                                                tx_dibits ? tx_dibits + (long long)c0 * tx_stride : nullptr, tx_stride);
         if (cudaGetLastError() != cudaSuccess) { return -1; }
         ++launches;

@@ -266,17 +266,18 @@ class Demodulator:
 
 def synth_capture(n_channels: int, n_samples: int, device: int = 0, snr_db: float = 30.0,
                   max_freq_off_hz: float = 300.0, min_amp: float = 0.05, max_amp: float = 2.0,
-                  seed_data: int = 12345, seed_noise: int = 777, first_channel: int = 0, want_tx: bool = False):
+                  seed_data: int = 12345, seed_noise: int = 777, first_channel: int = 0, want_tx: bool = False,
+                  want_iq: bool = True):
     """Synthetic TETRA-mapped pi/4-DQPSK capture generated in HBM (SURVEY.md 8d recipe).
-    Returns (iq [C][N][2] float32 cuda, tx_dibits [C][N/2+64] uint8 cuda | None)."""
+    Returns (iq [C][N][2] float32 cuda | None, tx_dibits [C][N/2+64] uint8 cuda | None)."""
     torch = _torch()
     dev = torch.device("cuda", device)
-    iq = torch.empty((n_channels, n_samples, 2), dtype=torch.float32, device=dev)
+    iq = torch.empty((n_channels, n_samples, 2), dtype=torch.float32, device=dev) if want_iq else None
     tx = torch.zeros((n_channels, n_samples // 2 + 64), dtype=torch.uint8, device=dev) if want_tx else None
     sp = capi.TdmSynthParams(snr_db, max_freq_off_hz, min_amp, max_amp, seed_data, seed_noise)
     stream = torch.cuda.current_stream(dev).cuda_stream
     capi.check(capi.lib().tdm_synth_capture(device, C.c_void_p(stream), C.byref(sp), n_channels, n_samples, n_samples,
-                                            first_channel, C.c_void_p(iq.data_ptr()),
+                                            first_channel, C.c_void_p(iq.data_ptr() if iq is not None else 0),
                                             C.c_void_p(tx.data_ptr() if tx is not None else 0),
                                             tx.shape[1] if tx is not None else 0), "tdm_synth_capture")
     return iq, tx

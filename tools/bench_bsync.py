@@ -27,17 +27,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
 
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--channels", type=int, default=4096)
-    ap.add_argument("--symbols", type=int, default=2_000_000)
-    ap.add_argument("--steps", type=int, default=5)
-    ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--call-bits", type=int, default=432)
-    ap.add_argument("--bits", action="store_true", help="feed one bit per byte (BitUnpacker output) instead of dibits")
-    ap.add_argument("--detect", action="store_true", help="also run the src/main.cpp:385-414 detector")
-    ap.add_argument("--no-cpu-baseline", action="store_true")
-    args = ap.parse_args()
+def measure(args):
 
     import numpy as np
     import torch
@@ -144,7 +134,7 @@ def main():
         cpu = {"value": round(reps_cpu * len(bits) / dtc / 1e6, 2), "unit": "Mbits/s", "cores": 1, "kind": kind,
                "sample": f"1 channel x {len(bits)} bits x {reps_cpu} passes, {what}; single thread (receiver state is process-global in the reference); {dtc:.1f} s"}
 
-    print(json.dumps({
+    return {
         "metric": "decoded Mbits/s through burst sync (tetra_burst_sync_in semantics)", "value": round(mbits, 1), "unit": "Mbits/s",
         "n_gpus": 1, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms, 3), "higher_is_better": True,
         "dtype": "u8", "data": "synthetic",
@@ -157,7 +147,25 @@ def main():
                      "frac": round(ach / peak, 4), "traffic": None, "peak_source": src,
                      "algorithmic_bytes_per_bit": bytes_per_bit},
         "cpu_baseline": cpu,
-    }))
+    }
+
+
+
+def parse_args(argv=None):
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--channels", type=int, default=4096)
+    ap.add_argument("--symbols", type=int, default=2_000_000)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--call-bits", type=int, default=432)
+    ap.add_argument("--bits", action="store_true", help="feed one bit per byte (BitUnpacker output) instead of dibits")
+    ap.add_argument("--detect", action="store_true", help="also run the src/main.cpp:385-414 detector")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args(argv)
+
+
+def main():
+    print(json.dumps(measure(parse_args())))
 
 
 if __name__ == "__main__":

@@ -23,16 +23,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
 
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--samples", type=int, default=1_000_000_000)
-    ap.add_argument("--channels", type=int, default=1)
-    ap.add_argument("--segments", type=int, default=4096)
-    ap.add_argument("--warmup", type=int, default=65536)
-    ap.add_argument("--steps", type=int, default=3)
-    ap.add_argument("--warmup-steps", type=int, default=1)
-    ap.add_argument("--no-cpu-baseline", action="store_true")
-    args = ap.parse_args()
+def measure(args):
 
     import numpy as np
     import torch
@@ -123,7 +114,7 @@ def main():
                          f"cannot use a second core for it); {what}; {dt:.1f} s"}
 
     value = C_ * N / (ms * 1e-3) / 1e6
-    print(json.dumps({
+    return {
         "metric": f"complex IQ Msamples/s through demod chain ({C_} channel{'s' if C_ > 1 else ''}, time-segmented)", "value": round(value, 1), "unit": "Msamples/s",
         "n_gpus": 1, "steps": args.steps, "warmup": args.warmup_steps, "ms_per_step": round(ms, 3), "higher_is_better": True,
         "dtype": "f32", "data": "synthetic",
@@ -135,7 +126,24 @@ def main():
         "plain_batch_call_msps": round(seq_msps, 2),
         "overhead_vs_batch_kernel": f"{info['warmup']}/{info['segment_samples']} warm-up samples redone per segment",
         "cpu_baseline": cpu,
-    }))
+    }
+
+
+
+def parse_args(argv=None):
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--samples", type=int, default=1_000_000_000)
+    ap.add_argument("--channels", type=int, default=1)
+    ap.add_argument("--segments", type=int, default=4096)
+    ap.add_argument("--warmup", type=int, default=65536)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup-steps", type=int, default=1)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args(argv)
+
+
+def main():
+    print(json.dumps(measure(parse_args())))
 
 
 if __name__ == "__main__":

@@ -21,12 +21,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
 
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--channels", type=int, default=64)
-    ap.add_argument("--chunk", type=int, default=32768)
-    ap.add_argument("--chunks", type=int, default=200)
-    args = ap.parse_args()
+def measure(args):
 
     import numpy as np
     import torch
@@ -112,7 +107,7 @@ def main():
         host_lat.append(dt * 1e3)
     host_lat.sort()
 
-    print(json.dumps({
+    return {
         "metric": "complex IQ Msamples/s through demod chain (streaming)", "unit": "Msamples/s", "n_gpus": 1,
         "config": {"workload": f"{C_} channels, {M} chunks of {K} samples, loop state carried across launches", "data": "synthetic"},
         "value": round(C_ * N / (dev_ms * 1e-3) / 1e6, 1),
@@ -124,7 +119,20 @@ def main():
                 "workload": "pinned host chunks via tdm_process(TDM_MEM_HOST), synchronous per chunk"},
         "chunked_equals_single_shot": same,
         "realtime_factor": round((C_ * N / (dev_ms * 1e-3)) / (C_ * 36000.0), 1),
-    }))
+    }
+
+
+
+def parse_args(argv=None):
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--channels", type=int, default=64)
+    ap.add_argument("--chunk", type=int, default=32768)
+    ap.add_argument("--chunks", type=int, default=200)
+    return ap.parse_args(argv)
+
+
+def main():
+    print(json.dumps(measure(parse_args())))
 
 
 if __name__ == "__main__":
