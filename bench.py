@@ -423,8 +423,15 @@ def main():
         #     rows in full and every other rank's rows by a position-weighted checksum the ranks computed from their own dibits
         if world > 1:
             w = torch.arange(1, S + 1, device=dev, dtype=torch.int64) % 65521
-            valid = torch.arange(S, device=dev)[None, :] < last.counts[:, None]
-            mysum = ((last.dibits.to(torch.int64) * w[None, :]) * valid).sum(dim=1)
+
+            def row_checksums(d, c):                          # position-weighted, 256 rows at a time (int64 temporaries)
+                parts = []
+                for r0 in range(0, d.shape[0], 256):
+                    v = torch.arange(S, device=dev)[None, :] < c[r0:r0 + 256][:, None]
+                    parts.append(((d[r0:r0 + 256, :S].to(torch.int64) * w[None, :]) * v).sum(dim=1))
+                return torch.cat(parts)
+
+            mysum = row_checksums(last.dibits, last.counts)
             sums = [torch.empty_like(mysum) for _ in range(world)] if rank == 0 else None
             dist.gather(mysum, sums, dst=0)
             if rank == 0:
@@ -433,13 +440,14 @@ def main():
                 for r0 in range(0, world * C_, 256):                  # 256 rows at a time: the unpacked form is 8 GB per rank
                     r1 = min(world * C_, r0 + 256)
                     ud, _ = dm.unpack_dibits(g_packed[r0:r1], g_counts[r0:r1], max_symbols=S, dibits=True)
-                    v = torch.arange(S, device=dev)[None, :] < g_counts[r0:r1][:, None]
-                    rs = ((ud[:, :S].to(torch.int64) * w[None, :]) * v).sum(dim=1)
+                    rs = row_checksums(ud, g_counts[r0:r1])
                     sent = torch.cat(sums)[r0:r1]
                     bad_rows += int((rs != sent).sum())
                     if r1 <= C_:                                      # rank 0's own rows: every dibit
+                        v = torch.arange(S, device=dev)[None, :] < g_counts[r0:r1][:, None]
                         bad_rows += int(((ud[:, :S] != last.dibits[r0:r1]) & v).any(dim=1).sum())
-                    del ud, v, rs
+                        del v
+                    del ud, rs
                 parity["gathered_over_nccl"] = {"rows": world * C_, "rows_differing_from_what_was_sent": bad_rows,
                                                 "how": "tdm_unpack_dibits on rank 0 vs each rank's own dibits (rank 0: every dibit; others: position-weighted checksums)"}
         # (3) an identical extra step from reset state vs the oracles on sampled channels, full length (rank 0)
@@ -527,6 +535,57 @@ def main():
                                   f"({-(-Cs // 32)} of 148 SMs busy per GPU: one recurrence warp per 32 channels, which is why this does not scale), "
                                   f"packed dibits gathered to rank 0 inside the step"}
             del so, sg
+        # the same workload time-segmented: every channel cut into overlapping segments so that the shard fills the GPU
+        # (tdm_process_long_batch: decoded dibits equal the sequential chain's from its lock point on -- the weaker contract)
+        try:
+            rows = 9472
+            with pkg.Demodulator(rows, max_chunk=1024, device=local_rank) as dl:
+                dl.use_torch_stream()
+                lo = torch.empty((Cs, N // 2 + 64), dtype=torch.uint8, device=dev)
+                lp = torch.empty((Cs, (N // 2 + 64 + 3) // 4), dtype=torch.uint8, device=dev)
+                lg = (torch.empty((world * Cs, lp.shape[1]), dtype=torch.uint8, device=dev), torch.empty(world * Cs, dtype=torch.int32, device=dev)) if rank == 0 else None
+                info = None
+
+                import ctypes as _C
+                Ct_ptr = lambda t: _C.c_void_p(t.data_ptr())
+                # tdm_pack_dibits packs the handle's n_channels rows: give it a handle-sized view by packing through a Cs-row handle
+                with pkg.Demodulator(Cs, max_chunk=1024, device=local_rank) as dpk:
+                    dpk.use_torch_stream()
+
+                    def lstep2():
+                        nonlocal info
+                        _, cnt64, info = dl.process_long_batch(view, out=lo)
+                        c32 = cnt64.to(torch.int32)
+                        capi.check(capi.lib().tdm_pack_dibits(dpk._h, Ct_ptr(lo), lo.shape[1], Ct_ptr(c32), Ct_ptr(lp), lp.shape[1]), "tdm_pack_dibits")
+                        comm.gather_packed(lp, c32, dst=0, out=lg, stream=torch.cuda.current_stream(dev))
+                        return c32
+
+                    dl.reset_all()
+                    lstep2()
+                    barrier()
+                    l0, l1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    l0.record()
+                    for i in range(args.steps):
+                        c32 = lstep2()
+                    l1.record()
+                    barrier()
+                    lt = torch.tensor([l0.elapsed_time(l1) / args.steps], dtype=torch.float64, device=dev)
+                    dist.all_reduce(lt, op=dist.ReduceOp.MAX)
+                    dl.reset_all()
+                    _, cnt64, info = dl.process_long_batch(view, out=lo)
+                    torch.cuda.synchronize()
+                    txe = tx_errors(pkg, torch, lo, cnt64, N, first_channel, local_rank, skip_frac=0.25)
+                    strong["time_segmented"] = {
+                        "value": round(STRONG_CHANNELS_TOTAL * N / (float(lt[0]) * 1e-3) / 1e6, 2), "unit": "Msamples/s", "ms_per_step": round(float(lt[0]), 3),
+                        "workload": f"the same {STRONG_CHANNELS_TOTAL} x {N} through tdm_process_long_batch: {Cs} channels per GPU as {info['n_segments']} segments of "
+                                    f"{info['segment_samples']} + {info['warmup']} warm-up samples ({Cs * info['n_segments']} rows per GPU), tdm_pack_dibits, "
+                                    f"tdm_gather_packed to rank 0, all inside the step",
+                        "contract": "decoded dibits equal the sequential chain's from its lock point on (include/tdm_b200.h)",
+                        "parity": {"rank0_channels_with_errors_vs_transmitted_last_three_quarters": txe["channels_with_errors"], "dibit_errors": txe["dibit_errors"],
+                                   "segments_redone": info["n_rerun"]}}
+                del lo, lp, lg
+        except Exception as e:                                   # must not take the headline down
+            strong["time_segmented"] = {"error": f"{type(e).__name__}: {e}"[:300]}
 
     # ---- end to end through the C ABI with host buffers
     e2e = None
