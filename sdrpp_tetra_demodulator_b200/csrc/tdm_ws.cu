@@ -119,14 +119,17 @@ __device__ __forceinline__ void xs_load_block(const WsSmem& sm, int slot, int la
 // busy ~90 % of a tick, so letting some run ahead moves no work off the critical resources, and the spin-waits cost
 // issue slots of their own.  The rendezvous stays.
 struct TickSync {
-    uint32_t bar;        // shared-memory address of the two mbarriers
+    uint32_t bar;        // shared-memory address of the two mbarriers (TDM_TICK_EVENTS builds)
     int lane;
+    int nthreads;        // threads of the CTA
 #ifdef TDM_ABLATE
     mutable long long t_wait = 0, t_mark = 0, t_total = 0;   // development builds: cycles spent waiting for events
 #endif
     __device__ __forceinline__ void arrive(int t) const {          // end of tick t (t >= -1)
 #ifndef TDM_TICK_EVENTS
-        asm volatile("bar.sync 0;" ::: "memory");
+        // the non-.aligned form with its thread count: warps arrive from DIFFERENT program counters (one tick loop per
+        // role), which `bar.sync` tolerates in hardware but compute-sanitizer's synccheck reads as divergence
+        asm volatile("barrier.sync 0, %0;" ::"r"(nthreads) : "memory");
         return;
 #endif
         __syncwarp();
@@ -155,8 +158,8 @@ struct TickSync {
 };
 __device__ __forceinline__ int last_tick(int nblk) { return nblk + 3; }   // ticks run t = -1 .. nblk + 3
 // Named barrier 1 links MID (arrives, does not wait) and LOOP (waits) once per tick: 64 threads.
-__device__ __forceinline__ void mid_arrive() { asm volatile("bar.arrive 1, 64;" ::: "memory"); }
-__device__ __forceinline__ void mid_wait() { asm volatile("bar.sync 1, 64;" ::: "memory"); }
+__device__ __forceinline__ void mid_arrive() { asm volatile("barrier.arrive 1, 64;" ::: "memory"); }
+__device__ __forceinline__ void mid_wait() { asm volatile("barrier.sync 1, 64;" ::: "memory"); }
 
 // fll_update without the out-of-range fallback: notes in `bad` that the exact path has to redo the tick.
 template <bool RE_ONLY>
@@ -277,7 +280,7 @@ __global__ void __launch_bounds__(Placement<PLACEMENT>::warps * 32, CTAS) demod_
         const float2* rh = reinterpret_cast<const float2*>(sp->r_hist);
         for (int j = 0; j < kITaps - 1; ++j) { sm.rs[j][lane] = rh[j]; }
     }
-    TickSync ts = { (uint32_t)__cvta_generic_to_shared(&sm.tickbar[0]), lane };
+    TickSync ts = { (uint32_t)__cvta_generic_to_shared(&sm.tickbar[0]), lane, NT };
 #ifdef TDM_ABLATE
     ts.t_mark = clock64();
 #endif

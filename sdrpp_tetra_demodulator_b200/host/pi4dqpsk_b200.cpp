@@ -1,42 +1,64 @@
 // pi4dqpsk_b200.cpp -- see pi4dqpsk_b200.h.  Host-side glue only: every output byte comes out of libtdm_b200.so.
 #include "pi4dqpsk_b200.h"
 
+#include <stdio.h>
 #include <string.h>
+#include <algorithm>
 
 namespace dsp::b200 {
 
-    void FusedQueue::push(FusedBatch&& b) {
+    void SymbolFifo::push(const uint8_t* data, int nsym, float standarderr, bool sync) {
         {
             std::lock_guard<std::mutex> lck(mtx);
-            q.emplace_back(std::move(b));
+            if (stopped) { return; }
+            q.insert(q.end(), data, data + (size_t)nsym * (size_t)width);
+            // nobody reading (no block wired behind, or it is not started): keep the newest kMaxSymbols
+            const size_t cap = kMaxSymbols * (size_t)width;
+            if (q.size() > cap) { q.erase(q.begin(), q.begin() + (long)(q.size() - cap)); }
+            lastErr = standarderr;
+            lastSync = sync;
         }
         cv.notify_all();
     }
-    bool FusedQueue::pop(FusedBatch& out) {
+    bool SymbolFifo::pop(uint8_t* out, int nsym, float* standarderr, bool* sync) {
+        const size_t need = (size_t)nsym * (size_t)width;
         std::unique_lock<std::mutex> lck(mtx);
-        cv.wait(lck, [this] { return !q.empty() || stopped; });
-        if (q.empty()) { return false; }
-        out = std::move(q.front());
-        q.pop_front();
+        cv.wait(lck, [&] { return q.size() >= need || stopped; });
+        if (q.size() < need) { return false; }
+        std::copy(q.begin(), q.begin() + (long)need, out);
+        q.erase(q.begin(), q.begin() + (long)need);
+        if (standarderr) { *standarderr = lastErr; }
+        if (sync) { *sync = lastSync; }
         return true;
     }
-    void FusedQueue::stop() {
+    void SymbolFifo::stop() {
         {
             std::lock_guard<std::mutex> lck(mtx);
             stopped = true;
         }
         cv.notify_all();
     }
-    void FusedQueue::restart() {
+    void SymbolFifo::restart() {
         std::lock_guard<std::mutex> lck(mtx);
         stopped = false;
         q.clear();
     }
+    void SymbolFifo::resume() {
+        std::lock_guard<std::mutex> lck(mtx);
+        stopped = false;
+    }
+
+    namespace {
+        thread_local PI4DQPSK* g_last_initialised = nullptr;
+    }
+    PI4DQPSK* PI4DQPSK::lastInitialised() { return g_last_initialised; }
 
     PI4DQPSK::~PI4DQPSK() {
         if (!base_type::_block_init) { return; }
         base_type::stop();
-        fused.stop();
+        dibitFifo.stop();
+        bitFifo.stop();
+        if (g_last_initialised == this) { g_last_initialised = nullptr; }
         tdm_destroy(handle);
         handle = nullptr;
     }
@@ -60,12 +82,17 @@ namespace dsp::b200 {
         device = dev;
         if (handle) { tdm_destroy(handle); handle = nullptr; }
         // one channel per block instance, buffers as large as an SDR++ stream buffer
-        tdm_create(&cfg, 1, STREAM_BUFFER_SIZE, device, &handle);
-        if (handle) {
+        const int rc = tdm_create(&cfg, 1, STREAM_BUFFER_SIZE, device, &handle);
+        if (rc != TDM_OK || !handle) {
+            // init() returns void in the reference: say why the block will not run instead of failing at the first buffer
+            handle = nullptr;
+            fprintf(stderr, "[tetra_demodulator b200] PI4DQPSK::init: tdm_create failed (%d): %s -- the block will not run\n", rc, tdm_last_error());
+        } else {
             const int64_t s = tdm_max_symbols(handle, STREAM_BUFFER_SIZE);
             dibitBuf.resize((size_t)s);
             bitBuf.resize((size_t)(2 * s));
         }
+        g_last_initialised = this;
         base_type::init(in);
     }
 
@@ -113,35 +140,28 @@ namespace dsp::b200 {
                              TDM_OUT_SYMBOLS | TDM_OUT_DIBITS | TDM_OUT_BITS, TDM_MEM_HOST);
         if (rc != TDM_OK) { return -1; }
         if (symCount > 0) {
-            FusedBatch b;
-            b.nsym = symCount;
-            b.dibits.assign(dibitBuf.begin(), dibitBuf.begin() + symCount);
-            b.bits.assign(bitBuf.begin(), bitBuf.begin() + 2 * (size_t)symCount);
             tdm_metrics m;
-            if (tdm_get_metrics(handle, &m, 1) == TDM_OK) { b.standarderr = m.standarderr; b.sync = m.sync != 0; }
-            fused.push(std::move(b));
+            float se = 0;
+            bool sy = false;
+            if (tdm_get_metrics(handle, &m, 1) == TDM_OK) { se = m.standarderr; sy = m.sync != 0; }
+            dibitFifo.push(dibitBuf.data(), symCount, se, sy);
+            bitFifo.push(bitBuf.data(), symCount, se, sy);
         }
         return symCount;
     }
 
-    // DQPSKSymbolExtractor::process (src/dsp/dqpsk_sym_extr.cpp:4-55): same count in, same count out.
+    // DQPSKSymbolExtractor::process (src/dsp/dqpsk_sym_extr.cpp:4-55): same count in, same count out.  The symbols in
+    // `in` are the fused launch's own output; their decisions were taken in the same launch and wait in the FIFO.
     int DQPSKSymbolExtractor::process(int count, const complex_t* in, uint8_t* out) {
         (void)in;
-        FusedBatch b;
-        if (!src || !src->fused.pop(b) || b.nsym != count) { return -1; }
-        memcpy(out, b.dibits.data(), (size_t)count);
-        sync = b.sync;
-        standarderr = b.standarderr;
-        unpacked.push(std::move(b));
+        if (!src || !src->dibitFifo.pop(out, count, &standarderr, &sync)) { return -1; }
         return count;
     }
 
     // BitUnpacker::process (src/dsp/bit_unpacker.cpp:4-10): returns count*2.
     int BitUnpacker::process(int count, const uint8_t* in, uint8_t* out) {
         (void)in;
-        FusedBatch b;
-        if (!src || !src->unpacked.pop(b) || b.nsym != count) { return -1; }
-        memcpy(out, b.bits.data(), 2 * (size_t)count);
+        if (!src || !src->bitFifo.pop(out, count, nullptr, nullptr)) { return -1; }
         return count * 2;
     }
 }

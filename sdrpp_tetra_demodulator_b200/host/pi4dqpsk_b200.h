@@ -14,14 +14,24 @@
 //     dsp::b200::BitUnpacker           : Processor<uint8_t, uint8_t>       (src/dsp/bit_unpacker.h:16-34)
 //
 // The GPU kernel is fused (one launch = demodulate + slice + decode + unpack), so PI4DQPSK keeps, next to the
-// complex symbols it puts on `out`, the dibits and bits of the same call in a side queue keyed by that call's
-// symbol count; the two downstream blocks pop from it instead of recomputing.  Their run() loops, stream
-// hand-offs and stop behaviour are the reference's own (same code shape as src/dsp/pi4dqpsk.h:38-50).
+// complex symbols it puts on `out`, the dibits and bits of the same symbols in two FIFOs indexed by CUMULATIVE
+// SYMBOL NUMBER; the two downstream blocks take as many entries as their input buffer holds symbols, whatever the
+// buffer boundaries are (a Reshaper or any other re-chunking block in between changes nothing).  Their run()
+// loops, stream hand-offs and stop behaviour are the reference's own (same code shape as src/dsp/pi4dqpsk.h:38-50).
+// PI4DQPSK::start() empties both FIFOs (buffers dropped by a stop()/start() cycle must not leave stale entries behind:
+// src/main.cpp enable()/disable() stop and start all blocks together; like in the reference, data in flight around a
+// stop is lost); a downstream block's stop() interrupts its own wait on the FIFO; a FIFO nobody reads is bounded (the
+// oldest entries are dropped).  Setters (tempStop/tempStart) leave the FIFOs alone.
 //
-// Everything below the class surface is the C ABI of libtdm_b200.so (include/tdm_b200.h).  If the library
-// reports an error, run() returns -1 and the worker thread ends -- the reference's only failure signal
-// (SURVEY.md 8b "Errors").  Built against SDR++ core headers in the plugin tree; against the stand-in headers
-// in oracle/sdrpp_standin for the tests here.
+// The downstream blocks keep the reference's init() signatures: init(in) binds to the PI4DQPSK most recently
+// initialised on the calling thread (src/main.cpp:84-91 initialises the three blocks of an instance back to back);
+// init(in, source) binds explicitly.
+//
+// Everything below the class surface is the C ABI of libtdm_b200.so (include/tdm_b200.h).  The reference's blocks
+// have no error codes (SURVEY.md 8b "Errors"): if the library cannot be brought up, init() says so on stderr,
+// ok() is false and run() returns -1, which ends the worker thread -- the reference's only failure signal.
+// Built against SDR++ core headers in the plugin tree; against the stand-in headers in oracle/sdrpp_standin for
+// the tests here.
 #pragma once
 #include <dsp/processor.h>
 
@@ -34,26 +44,25 @@
 
 namespace dsp::b200 {
 
-    // One fused call's slicer outputs, handed from PI4DQPSK to the extractor/unpacker blocks downstream.
-    struct FusedBatch {
-        int nsym = 0;
-        std::vector<uint8_t> dibits;   // nsym
-        std::vector<uint8_t> bits;     // 2*nsym
-        float standarderr = 0;
-        bool sync = false;
-    };
-
-    class FusedQueue {
+    // Slicer outputs of the fused launches as a stream: `width` bytes per symbol (1: dibits, 2: bits), first symbol
+    // number `head`.  One writer (PI4DQPSK::process), one reader (the block downstream).
+    class SymbolFifo {
     public:
-        void push(FusedBatch&& b);
-        // blocks until a batch is available or stop() was called; false on stop
-        bool pop(FusedBatch& out);
+        explicit SymbolFifo(int width_) : width(width_) {}
+        void push(const uint8_t* data, int nsym, float standarderr, bool sync);
+        // the next nsym symbols' bytes; blocks until they are there or stop() was called (false)
+        bool pop(uint8_t* out, int nsym, float* standarderr, bool* sync);
         void stop();
-        void restart();
+        void restart();                 // empty, accept data again (PI4DQPSK::start)
+        void resume();                  // accept data again, keep what is there (the reading block's start)
+        static constexpr size_t kMaxSymbols = 8u * 1000000u;   // 8 SDR++ stream buffers
     private:
+        const int width;
         std::mutex mtx;
         std::condition_variable cv;
-        std::deque<FusedBatch> q;
+        std::deque<uint8_t> q;
+        float lastErr = 0;
+        bool lastSync = false;
         bool stopped = false;
     };
 
@@ -104,9 +113,18 @@ namespace dsp::b200 {
         // returns the number of symbols written to `out`, or -1 if the GPU call failed
         int process(int count, const complex_t* in, complex_t* out);
 
-        // side channel for the fused slicer results (consumed by DQPSKSymbolExtractor below)
-        FusedQueue fused;
+        // side channels for the fused slicer results (consumed by DQPSKSymbolExtractor / BitUnpacker below)
+        SymbolFifo dibitFifo{ 1 };
+        SymbolFifo bitFifo{ 2 };
         const char* lastError() const;
+        bool ok() const { return handle != nullptr; }          // false: tdm_create failed in init(), run() returns -1
+        static PI4DQPSK* lastInitialised();                     // on the calling thread
+
+        void start() override {
+            dibitFifo.restart();
+            bitFifo.restart();
+            base_type::start();
+        }
 
     protected:
         void reconfigure();
@@ -122,6 +140,7 @@ namespace dsp::b200 {
     class DQPSKSymbolExtractor : public Processor<complex_t, uint8_t> {
         using base_type = Processor<complex_t, uint8_t>;
     public:
+        void init(stream<complex_t>* in) { init(in, PI4DQPSK::lastInitialised()); }      // src/dsp/dqpsk_sym_extr.h:27
         void init(stream<complex_t>* in, PI4DQPSK* source) {
             src = source;
             base_type::init(in);
@@ -138,11 +157,20 @@ namespace dsp::b200 {
             return outCount;
         }
         int process(int count, const complex_t* in, uint8_t* out);
+        PI4DQPSK* source() const { return src; }
 
         bool sync = false;
         float standarderr = 0;
-        // bits of the batch most recently handed out, for the BitUnpacker that follows
-        FusedQueue unpacked;
+
+    protected:
+        void doStart() override {
+            if (src) { src->dibitFifo.resume(); }
+            base_type::doStart();
+        }
+        void doStop() override {
+            if (src) { src->dibitFifo.stop(); }            // a worker waiting for dibits must see the stop
+            base_type::doStop();
+        }
 
     private:
         PI4DQPSK* src = nullptr;
@@ -152,7 +180,9 @@ namespace dsp::b200 {
     class BitUnpacker : public Processor<uint8_t, uint8_t> {
         using base_type = Processor<uint8_t, uint8_t>;
     public:
-        void init(stream<uint8_t>* in, DQPSKSymbolExtractor* source) {
+        void init(stream<uint8_t>* in) { init(in, PI4DQPSK::lastInitialised()); }         // src/dsp/bit_unpacker.h:24
+        void init(stream<uint8_t>* in, DQPSKSymbolExtractor* source) { init(in, source ? source->source() : nullptr); }
+        void init(stream<uint8_t>* in, PI4DQPSK* source) {
             src = source;
             base_type::init(in);
         }
@@ -169,7 +199,17 @@ namespace dsp::b200 {
         }
         int process(int count, const uint8_t* in, uint8_t* out);
 
+    protected:
+        void doStart() override {
+            if (src) { src->bitFifo.resume(); }
+            base_type::doStart();
+        }
+        void doStop() override {
+            if (src) { src->bitFifo.stop(); }
+            base_type::doStop();
+        }
+
     private:
-        DQPSKSymbolExtractor* src = nullptr;
+        PI4DQPSK* src = nullptr;
     };
 }

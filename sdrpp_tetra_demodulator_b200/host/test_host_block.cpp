@@ -4,7 +4,10 @@
 // unpacked bits to a file.  tests/test_host_block.py compares that file with the oracle's bits.
 //   usage: test_host_block <in.f32 (interleaved IQ)> <out.bits> <buffer_samples>
 #include <stdio.h>
+#include <string.h>
+#include <algorithm>
 #include <atomic>
+#include <chrono>
 #include <thread>
 #include <vector>
 #include "pi4dqpsk_b200.h"
@@ -30,11 +33,45 @@ int main(int argc, char** argv) {
     dsp::b200::BitUnpacker unpacker;
     demod.init(&vfo, c.symbolrate, c.samplerate, c.rrc_tap_count, c.rrc_beta, c.agc_rate, c.costas_bandwidth,
                c.fll_bandwidth, c.omega_gain, c.mu_gain, c.omega_rel_limit);
-    extractor.init(&demod.out, &demod);
-    unpacker.init(&extractor.out, &extractor);
+    // argv[4] == "rechunk": a thread between the demodulator and the extractor re-cuts the symbol stream into buffers of
+    // 1000 symbols (what a dsp::buffer::Reshaper does): the blocks must not depend on buffer boundaries
+    const bool rechunk = argc > 4 && !strcmp(argv[4], "rechunk");
+    const bool cycle = argc > 4 && !strcmp(argv[4], "cycle");
+    dsp::stream<dsp::complex_t> recut;
+    extractor.init(rechunk ? &recut : &demod.out);           // the reference's signatures (src/main.cpp:90-91)
+    unpacker.init(&extractor.out);
+    if (!demod.ok()) { fprintf(stderr, "demodulator not usable: %s\n", demod.lastError()); return 3; }
+    if (cycle) {
+        // enable() / disable() / enable() (src/main.cpp:105-114,132-163) with a buffer in flight: the second run must deliver
+        // a clean stream again (nothing stale, no worker lost)
+        demod.start(); extractor.start(); unpacker.start();
+        const int n0 = std::min<int>(chunk, (int)iq.size());
+        memcpy(vfo.writeBuf, iq.data(), sizeof(dsp::complex_t) * (size_t)n0);
+        vfo.swap(n0);                                         // consumed by the demodulator, its results are left in flight
+        std::this_thread::sleep_for(std::chrono::milliseconds(300));
+        demod.stop(); extractor.stop(); unpacker.stop();
+        demod.reset();
+    }
     demod.start();
     extractor.start();
     unpacker.start();
+    std::thread cutter;
+    if (rechunk) {
+        cutter = std::thread([&] {
+            std::vector<dsp::complex_t> pend;
+            while (true) {
+                int n = demod.out.read();
+                if (n < 0) { break; }
+                pend.insert(pend.end(), demod.out.readBuf, demod.out.readBuf + n);
+                demod.out.flush();
+                while (pend.size() >= 1000) {
+                    memcpy(recut.writeBuf, pend.data(), sizeof(dsp::complex_t) * 1000);
+                    if (!recut.swap(1000)) { return; }
+                    pend.erase(pend.begin(), pend.begin() + 1000);
+                }
+            }
+        });
+    }
 
     std::vector<uint8_t> bits;
     std::atomic<bool> done{ false };
@@ -61,6 +98,7 @@ int main(int argc, char** argv) {
     extractor.stop();
     unpacker.stop();
     unpacker.out.stopReader();
+    if (rechunk) { demod.out.stopReader(); recut.stopWriter(); cutter.join(); }
     sink.join();
 
     FILE* o = fopen(argv[2], "wb");

@@ -16,17 +16,18 @@ C_, N = 5, 3000
 iq = O.generate(C_, N)
 ob = O.OracleB(C_)
 cb, sb, db, bb = ob.process(iq, want_bits=True)
-for variant in (2, 5, 8):                      # tpc8, ws8b, ws3
+for variant in (2, 4, 8):                      # tpc8, ws4 (one CTA per SM), ws4 (two CTAs per SM build)
     with pkg.Demodulator(C_, N) as dm:
         dm.set_kernel_variant(variant)
-        r = dm.process(torch.from_numpy(iq).cuda(), symbols=True, dibits=True, bits=True)
+        r = dm.process(torch.from_numpy(iq).cuda(), symbols=True, dibits=True, bits=True, packed=True)
         torch.cuda.synchronize()
         assert np.array_equal(r.counts.cpu().numpy(), cb)
         assert all(np.array_equal(r.dibits[c, :cb[c]].cpu().numpy(), db[c, :cb[c]]) for c in range(C_)), variant
 with pkg.Demodulator(C_, 1000) as dm:          # host path with time slices + pack
     r = dm.process(iq[:, :1000].copy(), dibits=True)
     r2 = dm.process(torch.from_numpy(iq[:, 1000:]).cuda().contiguous(), dibits=True)
-    dm.pack_dibits(r2.dibits, r2.counts)
+    pk = dm.pack_dibits(r2.dibits, r2.counts)
+    dm.unpack_dibits(pk, r2.counts, dibits=True, bits=True)
     torch.cuda.synchronize()
 g, _ = pkg.synth_capture(2, 2000, want_tx=True)
 streams = [B.downlink_stream(5 + c, 6, ber=1e-3) for c in range(3)]
