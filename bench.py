@@ -679,6 +679,7 @@ def run_extra(torch, pkg):
     import bench_long
     import bench_streaming
     import bench_bsync
+    import bench_chan
     out = {}
 
     def guarded(name, fn):
@@ -718,6 +719,8 @@ def run_extra(torch, pkg):
     guarded("configs[2] 256 channels x 4e6 samples (plain call and tdm_process_long_batch)", batch_256)
     guarded("configs[4] streaming, 64 channels x 32768-sample chunks, state carried", streaming)
     guarded("burst sync after the path (4096 channels x 2e6 symbols)", bsync)
+    guarded("channeliser in front of the path (4608 channels from one 115.2 MS/s capture)",
+            lambda: bench_chan.measure(ap.Namespace(g=128, instants=16384, steps=3, warmup=1)))
     return out
 
 

@@ -1,0 +1,280 @@
+// tdm_chan.cu -- front-end channeliser: oversampled polyphase filterbank (include/tdm_chan_b200.h).
+//
+//   y_c[m] = sum_n h[n] x[t_m - n] e^{-j 2 pi c (t_m - n)/M},  t_m = (m+1) D - 1
+//          = sum_p e^{+j 2 pi c (p - r_m)/M} v_m[p],   v_m[p] = sum_{q<T} h[p + q M] x[t_m - p - q M],   r_m = t_m mod M
+// so one output instant = M branch sums (kernel below), rotated by r_m, then an M-point inverse DFT (cuFFT, batched
+// over instants, writing channel-major so the demodulator can read its rows in place).
+//
+// This stage is HBM-bound: per wideband sample 8 B are read once (the T * M / D re-reads of a sample by different
+// branch sums hit L2: the window an output tile needs is T M + tile D samples), the branch sums are written and read
+// once (8 B * M / D each) and the channel samples written once (8 B * M / D): 8 + 3 * 8 * 36/25 = 42.6 B per wideband
+// sample.  Arithmetic: 2 T FMAs per branch sum (T = 16: 32) + 5 log2 M flops per channel sample -- against 390 FMAs
+// per channel sample in the demodulator behind it.  Tensor cores: the DFT could be run as a [M x M] GEMM, but that is
+// 8 M / (5 log2 M) = 30 .. 600 times the FFT's flops and would have to be split-TF32 to keep fp32's dynamic range next
+// to a strong neighbour; an HBM-bound fp32 FFT is the right tool.
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <cmath>
+#include <cstring>
+#include <mutex>
+#include <new>
+#include <vector>
+#include "tdm_chan_b200.h"
+#include "tdm_b200.h"
+#include "tdm_internal.h"
+
+namespace {
+
+// ---- cuFFT, loaded at run time (only cufftPlanMany / ExecC2C / SetStream / Destroy of the public C API)
+typedef int cufftHandle;
+typedef int cufftResult;
+enum { CUFFT_C2C_ = 0x29, CUFFT_INVERSE_ = 1 };
+struct Cufft {
+    void* lib = nullptr;
+    cufftResult (*PlanMany)(cufftHandle*, int, int*, int*, int, int, int*, int, int, int, int) = nullptr;
+    cufftResult (*ExecC2C)(cufftHandle, float2*, float2*, int) = nullptr;
+    cufftResult (*SetStream)(cufftHandle, cudaStream_t) = nullptr;
+    cufftResult (*Destroy)(cufftHandle) = nullptr;
+    bool ok = false;
+};
+Cufft& cufft() {
+    static Cufft f;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        f.lib = dlopen("libcufft.so.11", RTLD_NOW | RTLD_GLOBAL);
+        if (!f.lib) { f.lib = dlopen("libcufft.so", RTLD_NOW | RTLD_GLOBAL); }
+        if (!f.lib) { return; }
+#define TDM_SYM(field, name) f.field = reinterpret_cast<decltype(f.field)>(dlsym(f.lib, name))
+        TDM_SYM(PlanMany, "cufftPlanMany");
+        TDM_SYM(ExecC2C, "cufftExecC2C");
+        TDM_SYM(SetStream, "cufftSetStream");
+        TDM_SYM(Destroy, "cufftDestroy");
+#undef TDM_SYM
+        f.ok = f.PlanMany && f.ExecC2C && f.SetStream && f.Destroy;
+    });
+    return f;
+}
+
+double bessel_i0(double x) {
+    double s = 1.0, t = 1.0;
+    for (int k = 1; k < 60; ++k) { t *= (x / (2.0 * k)) * (x / (2.0 * k)); s += t; if (t < 1e-18 * s) { break; } }
+    return s;
+}
+
+// Branch sums of a tile of output instants.  grid = (ceil(M / 256), ceil(n_out / kTile)), block = 256: thread = branch p,
+// looping over the tile's instants; the prototype taps of the branch (T values) live in registers for the whole tile.
+// x(i): i < 0 reads the carried history (the last T M samples of the previous calls), i >= 0 the new samples.
+// Loads are coalesced: consecutive branches read consecutive wideband samples (descending), stores likewise (rotated).
+constexpr int kTile = 16;
+template <int T>
+__global__ void __launch_bounds__(256) chan_polyphase_kernel(const float2* __restrict__ in, const float2* __restrict__ hist, long long n_hist,
+                                                             const float* __restrict__ taps, int M, int D, long long n_out,
+                                                             long long t0_global /* global index of in[0] */, float2* __restrict__ u) {
+    const int p = blockIdx.x * 256 + threadIdx.x;
+    if (p >= M) { return; }
+    float h[T];
+#pragma unroll
+    for (int q = 0; q < T; ++q) { h[q] = __ldg(taps + p + (long long)q * M); }
+    const long long m0 = (long long)blockIdx.y * kTile;
+    for (int i = 0; i < kTile; ++i) {
+        const long long m = m0 + i;
+        if (m >= n_out) { break; }
+        const long long tl = (m + 1) * D - 1;                 // newest sample of this instant, local index
+        float2 acc = make_float2(0.f, 0.f);
+#pragma unroll
+        for (int q = 0; q < T; ++q) {
+            const long long idx = tl - p - (long long)q * M;
+            const float2 x = idx >= 0 ? __ldg(in + idx) : hist[n_hist + idx];
+            acc.x = fmaf(h[q], x.x, acc.x);
+            acc.y = fmaf(h[q], x.y, acc.y);
+        }
+        const int r = (int)((t0_global + tl) % M);
+        int pp = p - r;
+        if (pp < 0) { pp += M; }
+        u[m * M + pp] = acc;
+    }
+}
+
+// the last n_hist samples of [hist | in] become the new history
+__global__ void chan_history_kernel(const float2* __restrict__ in, long long n_in, const float2* __restrict__ hist_old, float2* __restrict__ hist_new, long long n_hist) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n_hist; i += (long long)gridDim.x * blockDim.x) {
+        const long long src = n_in - n_hist + i;              // index into `in`; negative: old history
+        hist_new[i] = src >= 0 ? in[src] : hist_old[n_hist + src];
+    }
+}
+
+}  // namespace
+
+struct tdm_chan {
+    tdm_chan_config cfg{};
+    int device = 0;
+    std::vector<float> taps;
+    float* d_taps = nullptr;
+    float2* d_hist[2] = { nullptr, nullptr };
+    int cur = 0;
+    long long n_hist = 0;
+    long long t_global = 0;          // wideband samples consumed so far
+    float2* d_u = nullptr;
+    long long u_cap = 0;             // instants the branch-sum buffer holds
+    cufftHandle plan = 0;
+    long long plan_batch = 0, plan_stride = 0;
+    cudaEvent_t ev[3] = { nullptr, nullptr, nullptr };
+};
+
+extern "C" {
+
+int tdm_chan_default_config(int32_t g, tdm_chan_config* cfg) {
+    if (!cfg || g < 1) { return tdm_internal_fail(TDM_ERR_ARG, "tdm_chan_default_config: bad arguments"); }
+    std::memset(cfg, 0, sizeof(*cfg));
+    cfg->n_channels = 36 * g;            // 25 kHz raster ...
+    cfg->decimation = 25 * g;            // ... at 36 kS/s per channel (VFO_SAMPLERATE, src/main.cpp:35)
+    cfg->taps_per_branch = 16;
+    cfg->passband = 0.55;                // flat to +-13.75 kHz: a TETRA carrier occupies +-12.15 kHz (18 ksym/s, roll-off 0.35)
+    cfg->stopband = 0.89;                // 22.25 kHz: what folds onto the carrier's +-12.15 kHz at 36 kS/s starts at 36 - 12.15 = 23.85 kHz
+    cfg->stop_atten_db = 70.0;
+    return TDM_OK;
+}
+
+int tdm_chan_design(const tdm_chan_config* cfg, float* taps) {
+    if (!cfg || !taps) { return tdm_internal_fail(TDM_ERR_ARG, "tdm_chan_design: bad arguments"); }
+    const int M = cfg->n_channels, T = cfg->taps_per_branch;
+    if (M < 2 || T < 4 || T > 32 || cfg->decimation < 1 || cfg->decimation > M || !(cfg->passband > 0) || !(cfg->stopband > cfg->passband)) {
+        return tdm_internal_fail(TDM_ERR_UNSUPPORTED, "tdm_chan_design: need M >= 2, 4 <= T <= 32, 1 <= D <= M, 0 < passband < stopband");
+    }
+    const long long L = (long long)T * M;
+    const double A = cfg->stop_atten_db;
+    const double beta = A > 50 ? 0.1102 * (A - 8.7) : (A > 21 ? 0.5842 * std::pow(A - 21, 0.4) + 0.07886 * (A - 21) : 0.0);
+    const double fc = 0.5 * (cfg->passband + cfg->stopband) / M;          // cut-off in cycles per wideband sample
+    const double pi = 3.14159265358979323846, mid = 0.5 * (double)(L - 1);
+    double sum = 0.0;
+    std::vector<double> h((size_t)L);
+    for (long long n = 0; n < L; ++n) {
+        const double t = (double)n - mid;
+        const double s = t == 0.0 ? 2.0 * fc : std::sin(2.0 * pi * fc * t) / (pi * t);
+        const double a = t / (mid + 0.5);
+        const double w = bessel_i0(beta * std::sqrt(std::fmax(0.0, 1.0 - a * a))) / bessel_i0(beta);
+        h[(size_t)n] = s * w;
+        sum += h[(size_t)n];
+    }
+    for (long long n = 0; n < L; ++n) { taps[n] = (float)(h[(size_t)n] / sum); }
+    return TDM_OK;
+}
+
+int tdm_chan_create(const tdm_chan_config* cfg, int32_t device, tdm_chan** out) {
+    if (!out) { return tdm_internal_fail(TDM_ERR_ARG, "tdm_chan_create: out is null"); }
+    *out = nullptr;
+    tdm_chan_config local;
+    if (!cfg) { tdm_chan_default_config(4, &local); cfg = &local; }
+    const int M = cfg->n_channels, T = cfg->taps_per_branch;
+    std::vector<float> taps;
+    if (M >= 2 && T >= 4 && T <= 32) { taps.resize((size_t)T * (size_t)M); }
+    int rc = tdm_chan_design(cfg, taps.data());
+    if (rc != TDM_OK) { return rc; }
+    if (T != 8 && T != 12 && T != 16 && T != 24 && T != 32) { return tdm_internal_fail(TDM_ERR_UNSUPPORTED, "tdm_chan_create: taps_per_branch must be 8, 12, 16, 24 or 32"); }
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) { return tdm_internal_fail(TDM_ERR_NO_DEVICE, "tdm_chan_create: no CUDA device (this library has no CPU fallback)"); }
+    if (device < 0 || device >= ndev) { return tdm_internal_fail(TDM_ERR_ARG, "tdm_chan_create: device out of range"); }
+    if (!cufft().ok) { return tdm_internal_fail(TDM_ERR_UNSUPPORTED, "tdm_chan_create: libcufft.so.11 could not be loaded"); }
+    int prev = -1;
+    cudaGetDevice(&prev);
+    cudaSetDevice(device);
+    tdm_chan* c = new (std::nothrow) tdm_chan();
+    if (!c) { return tdm_internal_fail(TDM_ERR_NOMEM, "tdm_chan_create: out of host memory"); }
+    c->cfg = *cfg; c->device = device; c->taps = taps;
+    c->n_hist = (long long)T * M;
+    bool ok = cudaMalloc(&c->d_taps, sizeof(float) * taps.size()) == cudaSuccess &&
+              cudaMalloc(&c->d_hist[0], sizeof(float2) * (size_t)c->n_hist) == cudaSuccess &&
+              cudaMalloc(&c->d_hist[1], sizeof(float2) * (size_t)c->n_hist) == cudaSuccess &&
+              cudaMemcpy(c->d_taps, taps.data(), sizeof(float) * taps.size(), cudaMemcpyHostToDevice) == cudaSuccess &&
+              cudaMemset(c->d_hist[0], 0, sizeof(float2) * (size_t)c->n_hist) == cudaSuccess;
+    for (auto& e : c->ev) { ok = ok && cudaEventCreate(&e) == cudaSuccess; }
+    if (prev >= 0 && prev != device) { cudaSetDevice(prev); }
+    if (!ok) { tdm_chan_destroy(c); return tdm_internal_fail(TDM_ERR_NOMEM, "tdm_chan_create: device allocation failed"); }
+    *out = c;
+    return TDM_OK;
+}
+
+int tdm_chan_destroy(tdm_chan* c) {
+    if (!c) { return TDM_OK; }
+    int prev = -1;
+    cudaGetDevice(&prev);
+    cudaSetDevice(c->device);
+    if (c->plan && cufft().ok) { cufft().Destroy(c->plan); }
+    cudaFree(c->d_taps); cudaFree(c->d_hist[0]); cudaFree(c->d_hist[1]); cudaFree(c->d_u);
+    for (auto& e : c->ev) { if (e) { cudaEventDestroy(e); } }
+    if (prev >= 0 && prev != c->device) { cudaSetDevice(prev); }
+    delete c;
+    return TDM_OK;
+}
+
+int tdm_chan_reset(tdm_chan* c) {
+    if (!c) { return tdm_internal_fail(TDM_ERR_ARG, "null handle"); }
+    int prev = -1;
+    cudaGetDevice(&prev);
+    cudaSetDevice(c->device);
+    const bool ok = cudaMemset(c->d_hist[c->cur], 0, sizeof(float2) * (size_t)c->n_hist) == cudaSuccess;
+    if (prev >= 0 && prev != c->device) { cudaSetDevice(prev); }
+    c->t_global = 0;
+    return ok ? TDM_OK : tdm_internal_fail(TDM_ERR_CUDA, "tdm_chan_reset: memset failed");
+}
+
+int tdm_chan_process(tdm_chan* c, const float* wide, int64_t n_wide, float* out, int64_t out_stride, void* cuda_stream) {
+    if (!c || n_wide < 0 || (n_wide > 0 && (!wide || !out))) { return tdm_internal_fail(TDM_ERR_ARG, "tdm_chan_process: bad arguments"); }
+    const int M = c->cfg.n_channels, D = c->cfg.decimation, T = c->cfg.taps_per_branch;
+    if (n_wide % D) { return tdm_internal_fail(TDM_ERR_ARG, "tdm_chan_process: n_wide must be a multiple of the decimation %d", D); }
+    const long long n_out = n_wide / D;
+    if (n_out == 0) { return TDM_OK; }
+    if (out_stride < n_out) { return tdm_internal_fail(TDM_ERR_ARG, "tdm_chan_process: out_stride < n_wide / D"); }
+    if (n_out > 0x7fffffffLL) { return tdm_internal_fail(TDM_ERR_ARG, "tdm_chan_process: too many output instants for one call"); }
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    int prev = -1;
+    cudaGetDevice(&prev);
+    cudaSetDevice(c->device);
+    auto leave = [&](int code) { if (prev >= 0 && prev != c->device) { cudaSetDevice(prev); } return code; };
+    if (c->u_cap < n_out) {
+        cudaFree(c->d_u); c->d_u = nullptr; c->u_cap = 0;
+        if (cudaMalloc(&c->d_u, sizeof(float2) * (size_t)n_out * (size_t)M) != cudaSuccess) { return leave(tdm_internal_fail(TDM_ERR_NOMEM, "tdm_chan_process: cannot allocate the branch-sum buffer")); }
+        c->u_cap = n_out;
+    }
+    if (!c->plan || c->plan_batch != n_out || c->plan_stride != out_stride) {
+        if (c->plan) { cufft().Destroy(c->plan); c->plan = 0; }
+        int n[1] = { M }, inembed[1] = { M }, onembed[1] = { M };
+        // input: instant m at u + m M, unit stride; output: channel k of instant m at out + k * out_stride + m
+        if (out_stride > 0x7fffffffLL || cufft().PlanMany(&c->plan, 1, n, inembed, 1, M, onembed, (int)out_stride, 1, CUFFT_C2C_, (int)n_out) != 0) {
+            c->plan = 0;
+            return leave(tdm_internal_fail(TDM_ERR_CUDA, "tdm_chan_process: cufftPlanMany failed (M = %d, batch = %lld)", M, n_out));
+        }
+        c->plan_batch = n_out; c->plan_stride = out_stride;
+    }
+    const float2* in = reinterpret_cast<const float2*>(wide);
+    dim3 grid((unsigned)((M + 255) / 256), (unsigned)((n_out + kTile - 1) / kTile));
+    cudaEventRecord(c->ev[0], st);
+#define TDM_CHAN_LAUNCH(TT) chan_polyphase_kernel<TT><<<grid, 256, 0, st>>>(in, c->d_hist[c->cur], c->n_hist, c->d_taps, M, D, n_out, c->t_global, c->d_u)
+    switch (T) {
+        case 8: TDM_CHAN_LAUNCH(8); break;
+        case 12: TDM_CHAN_LAUNCH(12); break;
+        case 16: TDM_CHAN_LAUNCH(16); break;
+        case 24: TDM_CHAN_LAUNCH(24); break;
+        default: TDM_CHAN_LAUNCH(32); break;
+    }
+#undef TDM_CHAN_LAUNCH
+    cudaEventRecord(c->ev[1], st);
+    if (cufft().SetStream(c->plan, st) != 0 || cufft().ExecC2C(c->plan, c->d_u, reinterpret_cast<float2*>(out), CUFFT_INVERSE_) != 0) {
+        return leave(tdm_internal_fail(TDM_ERR_CUDA, "tdm_chan_process: cuFFT execution failed"));
+    }
+    cudaEventRecord(c->ev[2], st);
+    chan_history_kernel<<<256, 256, 0, st>>>(in, n_wide, c->d_hist[c->cur], c->d_hist[c->cur ^ 1], c->n_hist);
+    c->cur ^= 1;
+    c->t_global += n_wide;
+    if (cudaGetLastError() != cudaSuccess) { return leave(tdm_internal_fail(TDM_ERR_CUDA, "tdm_chan_process: kernel launch failed")); }
+    return leave(TDM_OK);
+}
+
+int tdm_chan_last_kernel_ms(tdm_chan* c, float* polyphase_ms, float* dft_ms) {
+    if (!c || !polyphase_ms || !dft_ms) { return tdm_internal_fail(TDM_ERR_ARG, "tdm_chan_last_kernel_ms: bad arguments"); }
+    if (cudaEventSynchronize(c->ev[2]) != cudaSuccess || cudaEventElapsedTime(polyphase_ms, c->ev[0], c->ev[1]) != cudaSuccess ||
+        cudaEventElapsedTime(dft_ms, c->ev[1], c->ev[2]) != cudaSuccess) { return tdm_internal_fail(TDM_ERR_CUDA, "tdm_chan_last_kernel_ms: no call timed yet"); }
+    return TDM_OK;
+}
+
+}  // extern "C"

@@ -28,7 +28,11 @@ def test_library_exports_every_declared_symbol(pkg):
     assert set(burst) == set(pkg.capi.EXPORTED_BURST_SYMBOLS), set(burst) ^ set(pkg.capi.EXPORTED_BURST_SYMBOLS)
     for name in burst:
         assert hasattr(L, name), f"{name} is declared in include/tdm_burst_b200.h but not exported"
-    assert sorted(os.listdir(os.path.join(ROOT, "include"))) == ["tdm_b200.h", "tdm_burst_b200.h"]
+    chan = _header_functions("tdm_chan_b200.h")
+    assert len(chan) == 7
+    for name in chan:
+        assert hasattr(L, name), f"{name} is declared in include/tdm_chan_b200.h but not exported"
+    assert sorted(os.listdir(os.path.join(ROOT, "include"))) == ["tdm_b200.h", "tdm_burst_b200.h", "tdm_chan_b200.h"]
 
 
 def test_library_has_sm100a_code_only(pkg):

@@ -1,0 +1,90 @@
+"""Front-end channeliser (include/tdm_chan_b200.h) on the GPU.
+
+PARITY UNPINNED BY THE REFERENCE (it has no channeliser: src/main.cpp:75 asks SDR++ for a VFO).  Checked against the
+float64 defining sum (oracle/oracle_chan.py) with tolerance 2e-5 of the output's RMS (fp32 accumulation over T M
+taps and an M-point fp32 FFT), for any chunking of the stream, and end to end: narrowband TETRA captures placed on the
+25 kHz raster of one wideband capture come back out of channeliser -> demodulator as the transmitted dibits."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def torch_cuda():
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    return torch
+
+
+def test_matches_the_defining_sum(pkg, torch_cuda):
+    torch = torch_cuda
+    from oracle import oracle_chan as OC
+    cfg = pkg.chan_default_config(2)             # M = 72, D = 50, T = 16
+    M, D = cfg.n_channels, cfg.decimation
+    h = pkg.chan_design(cfg)
+    rng = np.random.default_rng(3)
+    N = D * 400
+    x = (rng.standard_normal(N) + 1j * rng.standard_normal(N)).astype(np.complex64)
+    x += 30 * np.exp(2j * np.pi * (5.2 / M) * np.arange(N)).astype(np.complex64)          # a strong carrier near channel 5
+    wide = torch.from_numpy(np.stack([x.real, x.imag], axis=1).copy()).cuda()
+    with pkg.Channelizer(cfg) as ch:
+        y = ch.process(wide)
+        torch.cuda.synchronize()
+        got = y.cpu().numpy()
+        got = got[..., 0] + 1j * got[..., 1]
+        # the same stream in ragged calls (multiples of D) must give the same samples
+        ch.reset()
+        parts, pos = [], 0
+        for k in (1, 7, 64, 3, 325):
+            parts.append(ch.process(wide[pos:pos + k * D].contiguous()).cpu().numpy())
+            pos += k * D
+        torch.cuda.synchronize()
+        chunked = np.concatenate(parts, axis=1)
+        assert np.array_equal(chunked, y.cpu().numpy()), "chunked calls differ from the single call"
+    chans = [0, 1, 5, 6, 36, 71]
+    inst = [0, 1, 2, 17, 18, 150, 399]
+    want = OC.channelize_direct(x.astype(np.complex128), h.astype(np.float64), M, D, chans, inst)
+    rms = np.sqrt(np.mean(np.abs(got) ** 2))
+    err = np.abs(got[np.ix_(chans, inst)] - want).max()
+    assert err < 2e-5 * max(rms, 1.0), (err, rms)
+    # the strong carrier sits 0.2 of a channel off channel 5's centre: channel 40 (far away) must not see it
+    assert np.sqrt(np.mean(np.abs(got[40, 50:]) ** 2)) < 3.0
+
+
+def test_wideband_to_dibits_end_to_end(O, pkg, torch_cuda):
+    """6 TETRA carriers on a 144-channel raster (3.6 MS/s): wideband capture -> tdm_chan_process -> tdm_process (device buffers,
+    same stream, no host round trip) -> decoded dibits == transmitted dibits after the chain's lag, for every carrier."""
+    torch = torch_cuda
+    from oracle import oracle_chan as OC
+    cfg = pkg.chan_default_config(4)             # M = 144, D = 100
+    M, D = cfg.n_channels, cfg.decimation
+    n = 60000
+    carriers = [3, 4, 40, 71, 100, 143]          # 3 and 4 are neighbours on the raster: each sees the other's skirt inside +-18 kHz
+    sp = O.default_sg_params(snr_db=60.0, max_freq_off_hz=200.0, min_amp=0.5, max_amp=1.0)
+    nb = O.generate(len(carriers), n, sp)
+    narrow = nb[..., 0] + 1j * nb[..., 1]
+    wide = OC.place_on_raster(narrow, carriers, M, D)
+    rng = np.random.default_rng(1)
+    wide += 1e-3 * (rng.standard_normal(len(wide)) + 1j * rng.standard_normal(len(wide)))
+    w = torch.from_numpy(np.stack([wide.real, wide.imag], axis=1).astype(np.float32)).cuda()
+    with pkg.Channelizer(cfg) as ch, pkg.Demodulator(M, n) as dm:
+        dm.use_torch_stream()
+        y = ch.process(w)                          # [M][n][2] in HBM
+        r = dm.process(y, dibits=True)             # every channel of the raster, occupied or not
+        torch.cuda.synchronize()
+        counts, dib = r.counts.cpu().numpy(), r.dibits.cpu().numpy()
+        sync = dm.metrics()["sync"]
+    for k, c in enumerate(carriers):
+        tx = O.tx_dibits(k, n)
+        cnt = int(counts[c])
+        # the reference's loops can take more than 10^4 symbols to settle at an unlucky timing phase (the golden fixtures'
+        # lock indices show the same; reproduced with the float64 channeliser + the CPU checker for the carrier on channel
+        # 40, last error at symbol 13702): the property is stated on the last third of the capture
+        first = 20000
+        errs = {lag: np.flatnonzero(dib[c, lag + first:cnt - 8] != tx[first:cnt - 8 - lag]) for lag in range(10, 60)}
+        lag = min(errs, key=lambda k: len(errs[k]))
+        assert len(errs[lag]) == 0, f"carrier on channel {c}: {len(errs[lag])} dibit errors after symbol {first} (lag {lag}), at {errs[lag][:8] + first}"
+        assert sync[c] == 1
+    assert sync[[20, 50, 120]].sum() == 0          # empty channels do not report lock
