@@ -254,8 +254,28 @@ int tdm_set_state(tdm_handle* h, const tdm_channel_state* host_states, int32_t n
 /* DQPSKSymbolExtractor::sync / ::standarderr for every channel (src/dsp/dqpsk_sym_extr.h:35-36). */
 int tdm_get_metrics(tdm_handle* h, tdm_metrics* host_metrics, int32_t n_channels);
 
-/* The setters of PI4DQPSK (src/dsp/pi4dqpsk.h:52-63): redo the host-side design
- * and upload it; loop state is left alone, like the reference's setters. */
+/* The setters of PI4DQPSK (src/dsp/pi4dqpsk.h:52-63), with the reference's own (partial) effects
+ * (src/dsp/pi4dqpsk.cpp:31-118).  `cfg` is the complete new configuration, `what` says which setter ran:
+ *   TDM_SET_RATES        setSymbolrate / setSamplerate: new RRC taps AND the timing loop restarted as
+ *                        COMPLEX_FD::setOmega does (offset 0, mu 0, omega = samplerate/symbolrate, limits from
+ *                        the current omega_rel_limit; complex_fd.cpp:31-42).  The band-edge filters of the FLL
+ *                        are NOT redesigned -- the reference never calls fll.setSymbolrate/setSamplerate
+ *                        from these setters (pi4dqpsk.cpp:31-55)
+ *   TDM_SET_RRC          setRRCParams / setRRCTapCount / setRRCBeta: new RRC taps only (pi4dqpsk.cpp:57-75)
+ *   TDM_SET_AGC_RATE     setAGCRate (agc.setRate)
+ *   TDM_SET_COSTAS_BW    setCostasBandwidth (PLL::setBandwidth: alpha, beta)
+ *   TDM_SET_FLL_BW       setFllBandwidth (fll.cpp setBandwidth: beta; alpha stays 0)
+ *   TDM_SET_TIMING_GAINS setMMParams / setOmegaGain / setMuGain / setOmegaRelLimit: loop gains and the omega limits
+ *                        omega (1 -+ omega_rel_limit) (complex_fd.cpp:44-61); the loop's state is not touched
+ * Loop state other than the timing restart above is left alone.  tdm_set_config = everything at once, as a fresh
+ * init() would design it (band-edge filters included), with the timing restart when the rates changed. */
+#define TDM_SET_RATES 1u
+#define TDM_SET_RRC 2u
+#define TDM_SET_AGC_RATE 4u
+#define TDM_SET_COSTAS_BW 8u
+#define TDM_SET_FLL_BW 16u
+#define TDM_SET_TIMING_GAINS 32u
+int tdm_set_params(tdm_handle* h, const tdm_config* cfg, uint32_t what);
 int tdm_set_config(tdm_handle* h, const tdm_config* cfg);
 int tdm_get_design(const tdm_handle* h, tdm_design* out);
 

@@ -183,6 +183,32 @@ class OracleB:
         for c in range(n_channels):
             self.L.ob_state_init(C.byref(self.design), self.states[c:c + 1].ctypes.data_as(C.c_void_p))
 
+    def set_params(self, cfg: TdmConfig, what: int):
+        """tdm_set_params' contract (include/tdm_b200.h TDM_SET_*), restated: which parts of the design a setter of
+        the reference replaces (src/dsp/pi4dqpsk.cpp:31-118), plus COMPLEX_FD::setOmega's restart for the rates."""
+        d = TdmDesign()
+        rc = self.L.ob_design(C.byref(cfg), C.byref(d))
+        if rc != 0:
+            raise ValueError(f"ob_design failed: {rc}")
+        cur = self.design
+        if what & (1 | 2):
+            cur.rrc, cur.ntaps = d.rrc, d.ntaps
+        if what & 4:
+            cur.agc_rate = d.agc_rate
+        if what & 8:
+            cur.costas_alpha, cur.costas_beta = d.costas_alpha, d.costas_beta
+        if what & 16:
+            cur.fll_beta = d.fll_beta
+        if what & 32:
+            cur.tr_alpha, cur.tr_beta = d.tr_alpha, d.tr_beta
+            cur.tr_min_omega, cur.tr_max_omega = d.tr_min_omega, d.tr_max_omega
+        if what & 1:
+            cur.tr_init_omega, cur.tr_min_omega, cur.tr_max_omega = d.tr_init_omega, d.tr_min_omega, d.tr_max_omega
+            self.states["tr_offset"] = 0
+            self.states["tr_mu"] = 0
+            self.states["tr_omega"] = d.tr_init_omega
+        self.cfg = cfg
+
     @staticmethod
     def default_config() -> TdmConfig:
         cfg = TdmConfig()
@@ -235,6 +261,7 @@ def lib_a(fastamp_re_only: bool = False) -> C.CDLL:
         L.tref_process.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.tref_process.restype = C.c_int64
         L.tref_get_state.argtypes = [C.c_void_p, C.POINTER(TrefLoopState)]
+        L.tref_set.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_double, C.c_double]
         L.tref_get_taps.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                     C.POINTER(C.c_int), C.POINTER(C.c_int)]
         L.tref_get_taps.restype = C.c_int
@@ -289,6 +316,11 @@ class OracleA:
         arr = (C.c_void_p * Cn)(*self.handles)
         self.L.tref_process_multi(arr, Cn, N, _ptr(iq), _ptr(dibits), S, _ptr(counts), nthreads)
         return counts, dibits
+
+    def set(self, what: int, a: float, b: float = 0.0, c: float = 0.0):
+        """the reference's own setters on every chain (ref_driver.cpp tref_set: 1 setSymbolrate .. 10 setMuGain)"""
+        for h in self.handles:
+            self.L.tref_set(h, int(what), float(a), float(b), float(c))
 
     def loop_state(self, c: int = 0) -> TrefLoopState:
         s = TrefLoopState()

@@ -142,6 +142,26 @@ int64_t tref_process(void* h, int64_t count, const float* iq, float* syms, uint8
     return nsym;
 }
 
+// The reference's own setters (src/dsp/pi4dqpsk.h:52-63), for pinning tdm_set_params:
+//   1 setSymbolrate(a)  2 setSamplerate(a)  3 setRRCParams(int(a), b)  4 setAGCRate(a)  5 setCostasBandwidth(a)
+//   6 setFllBandwidth(a)  7 setMMParams(a, b, c)  8 setOmegaRelLimit(a)  9 setOmegaGain(a)  10 setMuGain(a)
+void tref_set(void* h, int what, double a, double b, double c3) {
+    tref_chain* c = (tref_chain*)h;
+    switch (what) {
+        case 1: c->demod.setSymbolrate(a); break;
+        case 2: c->demod.setSamplerate(a); break;
+        case 3: c->demod.setRRCParams((int)a, b); break;
+        case 4: c->demod.setAGCRate(a); break;
+        case 5: c->demod.setCostasBandwidth(a); break;
+        case 6: c->demod.setFllBandwidth(a); break;
+        case 7: c->demod.setMMParams(a, b, c3); break;
+        case 8: c->demod.setOmegaRelLimit(a); break;
+        case 9: c->demod.setOmegaGain(a); break;
+        case 10: c->demod.setMuGain(a); break;
+        default: break;
+    }
+}
+
 void tref_get_state(void* h, tref_loop_state* s) {
     tref_chain* c = (tref_chain*)h;
     s->agc_gain = c->demod.agc._gain;

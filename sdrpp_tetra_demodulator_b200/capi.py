@@ -35,6 +35,7 @@ TDM_OUT_DIBITS = 2
 TDM_OUT_BITS = 4
 TDM_OUT_PACKED = 8
 TDM_CFG_FASTAMP_RE_ONLY = 1
+TDM_SET_RATES, TDM_SET_RRC, TDM_SET_AGC_RATE, TDM_SET_COSTAS_BW, TDM_SET_FLL_BW, TDM_SET_TIMING_GAINS = 1, 2, 4, 8, 16, 32
 
 # every symbol include/tdm_b200.h declares (tests check the library exports each one)
 EXPORTED_SYMBOLS = [
@@ -43,7 +44,7 @@ EXPORTED_SYMBOLS = [
     "tdm_get_metrics", "tdm_set_config", "tdm_get_design", "tdm_set_kernel_variant", "tdm_last_kernel_ms",
     "tdm_launch_count", "tdm_pack_dibits", "tdm_synth_capture", "tdm_last_error", "tdm_abi_version",
     "tdm_process_long", "tdm_process_long_batch", "tdm_process_io", "tdm_unpack_dibits",
-    "tdm_comm_unique_id", "tdm_comm_create", "tdm_comm_adopt", "tdm_comm_destroy", "tdm_gather_packed",
+    "tdm_set_params", "tdm_comm_unique_id", "tdm_comm_create", "tdm_comm_adopt", "tdm_comm_destroy", "tdm_gather_packed",
 ]
 # ... and include/tdm_burst_b200.h
 EXPORTED_BURST_SYMBOLS = [
@@ -173,6 +174,7 @@ def lib() -> C.CDLL:
         "tdm_set_state": (C.c_int, [vp, vp, i32]),
         "tdm_get_metrics": (C.c_int, [vp, vp, i32]),
         "tdm_set_config": (C.c_int, [vp, C.POINTER(TdmConfig)]),
+        "tdm_set_params": (C.c_int, [vp, C.POINTER(TdmConfig), u32]),
         "tdm_get_design": (C.c_int, [vp, C.POINTER(TdmDesign)]),
         "tdm_set_kernel_variant": (C.c_int, [vp, i32]),
         "tdm_last_kernel_ms": (C.c_int, [vp, C.POINTER(C.c_float)]),

@@ -658,6 +658,47 @@ int tdm_get_metrics(tdm_handle* h, tdm_metrics* m, int32_t n_channels) {
     return TDM_OK;
 }
 
+namespace {
+// COMPLEX_FD::setOmega (complex_fd.cpp:31-42): offset = 0, pcl.phase = 0, pcl.freq = omega for every channel
+int restart_timing(tdm_handle* h) {
+    std::vector<tdm_channel_state> st((size_t)h->n_channels);
+    int rc = tdm_get_state(h, st.data(), h->n_channels);
+    if (rc != TDM_OK) { return rc; }
+    for (auto& s : st) { s.tr_offset = 0; s.tr_mu = 0; s.tr_omega = h->design.tr_init_omega; }
+    return tdm_set_state(h, st.data(), h->n_channels);
+}
+}  // namespace
+
+int tdm_set_params(tdm_handle* h, const tdm_config* cfg, uint32_t what) {
+    if (!h || !cfg) { return fail(TDM_ERR_ARG, "tdm_set_params: bad arguments"); }
+    if (what & ~(TDM_SET_RATES | TDM_SET_RRC | TDM_SET_AGC_RATE | TDM_SET_COSTAS_BW | TDM_SET_FLL_BW | TDM_SET_TIMING_GAINS)) {
+        return fail(TDM_ERR_ARG, "tdm_set_params: unknown bits in `what`");
+    }
+    tdm_design d;
+    int rc = tdm_design_from_config(cfg, &d);
+    if (rc != TDM_OK) { return fail(rc, "tdm_set_params: configuration not supported"); }
+    DeviceGuard guard(h->device);
+    TDM_CUDA(cudaStreamSynchronize(h->stream));
+    tdm_design& cur = h->design;
+    if (what & (TDM_SET_RATES | TDM_SET_RRC)) { std::memcpy(cur.rrc, d.rrc, sizeof(cur.rrc)); cur.ntaps = d.ntaps; }
+    if (what & TDM_SET_AGC_RATE) { cur.agc_rate = d.agc_rate; }
+    if (what & TDM_SET_COSTAS_BW) { cur.costas_alpha = d.costas_alpha; cur.costas_beta = d.costas_beta; }
+    if (what & TDM_SET_FLL_BW) { cur.fll_beta = d.fll_beta; }
+    if (what & TDM_SET_TIMING_GAINS) { cur.tr_alpha = d.tr_alpha; cur.tr_beta = d.tr_beta; cur.tr_min_omega = d.tr_min_omega; cur.tr_max_omega = d.tr_max_omega; }
+    h->cfg = *cfg;
+    if (what & TDM_SET_RATES) {
+        cur.tr_init_omega = d.tr_init_omega; cur.tr_min_omega = d.tr_min_omega; cur.tr_max_omega = d.tr_max_omega;
+        const long long ms = max_symbols_for(cur, h->max_chunk);
+        if (ms > h->max_syms) {          // staging rows sized for the old rate are too short now: re-made lazily
+            cudaFree(h->d_syms); cudaFree(h->d_dibits); cudaFree(h->d_bits); cudaFree(h->d_packed);
+            h->d_syms = nullptr; h->d_dibits = nullptr; h->d_bits = nullptr; h->d_packed = nullptr;
+        }
+        h->max_syms = ms > h->max_syms ? ms : h->max_syms;
+        return restart_timing(h);
+    }
+    return TDM_OK;
+}
+
 int tdm_set_config(tdm_handle* h, const tdm_config* cfg) {
     if (!h || !cfg) { return fail(TDM_ERR_ARG, "tdm_set_config: bad arguments"); }
     tdm_design d;
@@ -665,13 +706,19 @@ int tdm_set_config(tdm_handle* h, const tdm_config* cfg) {
     if (rc != TDM_OK) { return fail(rc, "tdm_set_config: configuration not supported"); }
     DeviceGuard guard(h->device);
     TDM_CUDA(cudaStreamSynchronize(h->stream));
+    const bool rates_changed = cfg->samplerate != h->cfg.samplerate || cfg->symbolrate != h->cfg.symbolrate;
     h->cfg = *cfg;
     h->design = d;
-    h->max_syms = max_symbols_for(d, h->max_chunk);
-    // staging sized from the old design may be too small now: drop it, it is re-made lazily
-    cudaFree(h->d_syms); cudaFree(h->d_dibits); cudaFree(h->d_bits); cudaFree(h->d_packed);
-    h->d_syms = nullptr; h->d_dibits = nullptr; h->d_bits = nullptr; h->d_packed = nullptr;
-    return upload_design(h);
+    const long long ms = max_symbols_for(d, h->max_chunk);
+    if (ms > h->max_syms) {
+        // staging sized from the old design is too small now: drop it, it is re-made lazily
+        cudaFree(h->d_syms); cudaFree(h->d_dibits); cudaFree(h->d_bits); cudaFree(h->d_packed);
+        h->d_syms = nullptr; h->d_dibits = nullptr; h->d_bits = nullptr; h->d_packed = nullptr;
+        h->max_syms = ms;
+    }
+    rc = upload_design(h);
+    if (rc != TDM_OK) { return rc; }
+    return rates_changed ? restart_timing(h) : TDM_OK;
 }
 
 int tdm_get_design(const tdm_handle* h, tdm_design* out) {

@@ -88,6 +88,11 @@ class Demodulator:
         capi.check(self._lib.tdm_set_config(self._h, C.byref(config)), "tdm_set_config")
         self.config = config
 
+    def set_params(self, config: capi.TdmConfig, what: int) -> None:
+        """one of PI4DQPSK's setters with the reference's partial effect (tdm_set_params, capi.TDM_SET_*)"""
+        capi.check(self._lib.tdm_set_params(self._h, C.byref(config), int(what)), "tdm_set_params")
+        self.config = config
+
     def set_kernel_variant(self, variant: int) -> None:
         capi.check(self._lib.tdm_set_kernel_variant(self._h, int(variant)), "tdm_set_kernel_variant")
 
@@ -328,26 +333,26 @@ class PI4DQPSK:
     def reset(self):
         self._need().reset()
 
-    # setters, src/dsp/pi4dqpsk.h:52-63 -- each redoes the host-side design and leaves loop state alone
-    def _reconfigure(self, **kw):
+    # setters, src/dsp/pi4dqpsk.h:52-63 -- each with the reference's own partial effect (src/dsp/pi4dqpsk.cpp:31-118)
+    def _set(self, what, **kw):
         dm = self._need()
         for k, v in kw.items():
             setattr(self._cfg, k, v)
-        dm.set_config(self._cfg)
+        dm.set_params(self._cfg, what)
 
-    def setSymbolrate(self, symbolrate): self._reconfigure(symbolrate=symbolrate)
-    def setSamplerate(self, samplerate): self._reconfigure(samplerate=samplerate)
-    def setRRCParams(self, rrcTapCount, rrcBeta): self._reconfigure(rrc_tap_count=int(rrcTapCount), rrc_beta=rrcBeta)
-    def setRRCTapCount(self, rrcTapCount): self._reconfigure(rrc_tap_count=int(rrcTapCount))
-    def setRRCBeta(self, rrcBeta): self._reconfigure(rrc_beta=rrcBeta)
-    def setAGCRate(self, agcRate): self._reconfigure(agc_rate=agcRate)
-    def setCostasBandwidth(self, bandwidth): self._reconfigure(costas_bandwidth=bandwidth)
-    def setFllBandwidth(self, fllBandwidth): self._reconfigure(fll_bandwidth=fllBandwidth)
+    def setSymbolrate(self, symbolrate): self._set(capi.TDM_SET_RATES, symbolrate=symbolrate)
+    def setSamplerate(self, samplerate): self._set(capi.TDM_SET_RATES, samplerate=samplerate)
+    def setRRCParams(self, rrcTapCount, rrcBeta): self._set(capi.TDM_SET_RRC, rrc_tap_count=int(rrcTapCount), rrc_beta=rrcBeta)
+    def setRRCTapCount(self, rrcTapCount): self._set(capi.TDM_SET_RRC, rrc_tap_count=int(rrcTapCount))
+    def setRRCBeta(self, rrcBeta): self._set(capi.TDM_SET_RRC, rrc_beta=int(rrcBeta))          # int, like the reference ([A.9])
+    def setAGCRate(self, agcRate): self._set(capi.TDM_SET_AGC_RATE, agc_rate=agcRate)
+    def setCostasBandwidth(self, bandwidth): self._set(capi.TDM_SET_COSTAS_BW, costas_bandwidth=bandwidth)
+    def setFllBandwidth(self, fllBandwidth): self._set(capi.TDM_SET_FLL_BW, fll_bandwidth=fllBandwidth)
     def setMMParams(self, omegaGain, muGain, omegaRelLimit=0.01):
-        self._reconfigure(omega_gain=omegaGain, mu_gain=muGain, omega_rel_limit=omegaRelLimit)
-    def setOmegaGain(self, omegaGain): self._reconfigure(omega_gain=omegaGain)
-    def setMuGain(self, muGain): self._reconfigure(mu_gain=muGain)
-    def setOmegaRelLimit(self, omegaRelLimit): self._reconfigure(omega_rel_limit=omegaRelLimit)
+        self._set(capi.TDM_SET_TIMING_GAINS, omega_gain=omegaGain, mu_gain=muGain, omega_rel_limit=omegaRelLimit)
+    def setOmegaGain(self, omegaGain): self._set(capi.TDM_SET_TIMING_GAINS, omega_gain=omegaGain)
+    def setMuGain(self, muGain): self._set(capi.TDM_SET_TIMING_GAINS, mu_gain=muGain)
+    def setOmegaRelLimit(self, omegaRelLimit): self._set(capi.TDM_SET_TIMING_GAINS, omega_rel_limit=omegaRelLimit)
 
 
 class DQPSKSymbolExtractor:

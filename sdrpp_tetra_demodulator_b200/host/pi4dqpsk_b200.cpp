@@ -98,28 +98,32 @@ namespace dsp::b200 {
 
     const char* PI4DQPSK::lastError() const { return tdm_last_error(); }
 
-    // the reference's setters stop the worker, mutate, restart (src/dsp/pi4dqpsk.cpp:32-118)
-    void PI4DQPSK::reconfigure() {
+    // The reference's setters (src/dsp/pi4dqpsk.cpp:31-118): the rate/RRC ones stop the worker, mutate, restart; the
+    // coefficient ones only take ctrlMtx and write a float the worker reads.  Here every setter pauses the worker:
+    // the handle is single-caller and the new design must not be swapped under a running tdm_process.  The EFFECT of
+    // each setter is the reference's (tdm_set_params): e.g. setSymbolrate redesigns the RRC taps and restarts the
+    // timing loop but leaves the band-edge filters alone.
+    void PI4DQPSK::reconfigure(uint32_t what) {
         assert(base_type::_block_init);
         std::lock_guard<std::recursive_mutex> lck(base_type::ctrlMtx);
         base_type::tempStop();
-        if (handle) { tdm_set_config(handle, &cfg); }
+        if (handle) { tdm_set_params(handle, &cfg, what); }
         base_type::tempStart();
     }
-    void PI4DQPSK::setSymbolrate(double symbolrate) { cfg.symbolrate = symbolrate; reconfigure(); }
-    void PI4DQPSK::setSamplerate(double samplerate) { cfg.samplerate = samplerate; reconfigure(); }
-    void PI4DQPSK::setRRCParams(int rrcTapCount, double rrcBeta) { cfg.rrc_tap_count = rrcTapCount; cfg.rrc_beta = rrcBeta; reconfigure(); }
+    void PI4DQPSK::setSymbolrate(double symbolrate) { cfg.symbolrate = symbolrate; reconfigure(TDM_SET_RATES); }
+    void PI4DQPSK::setSamplerate(double samplerate) { cfg.samplerate = samplerate; reconfigure(TDM_SET_RATES); }
+    void PI4DQPSK::setRRCParams(int rrcTapCount, double rrcBeta) { cfg.rrc_tap_count = rrcTapCount; cfg.rrc_beta = rrcBeta; reconfigure(TDM_SET_RRC); }
     void PI4DQPSK::setRRCTapCount(int rrcTapCount) { setRRCParams(rrcTapCount, cfg.rrc_beta); }
     void PI4DQPSK::setRRCBeta(int rrcBeta) { setRRCParams(cfg.rrc_tap_count, rrcBeta); }
-    void PI4DQPSK::setAGCRate(double agcRate) { cfg.agc_rate = agcRate; reconfigure(); }
-    void PI4DQPSK::setCostasBandwidth(double bandwidth) { cfg.costas_bandwidth = bandwidth; reconfigure(); }
-    void PI4DQPSK::setFllBandwidth(double fllBandwidth) { cfg.fll_bandwidth = fllBandwidth; reconfigure(); }
+    void PI4DQPSK::setAGCRate(double agcRate) { cfg.agc_rate = agcRate; reconfigure(TDM_SET_AGC_RATE); }
+    void PI4DQPSK::setCostasBandwidth(double bandwidth) { cfg.costas_bandwidth = bandwidth; reconfigure(TDM_SET_COSTAS_BW); }
+    void PI4DQPSK::setFllBandwidth(double fllBandwidth) { cfg.fll_bandwidth = fllBandwidth; reconfigure(TDM_SET_FLL_BW); }
     void PI4DQPSK::setMMParams(double omegaGain, double muGain, double omegaRelLimit) {
-        cfg.omega_gain = omegaGain; cfg.mu_gain = muGain; cfg.omega_rel_limit = omegaRelLimit; reconfigure();
+        cfg.omega_gain = omegaGain; cfg.mu_gain = muGain; cfg.omega_rel_limit = omegaRelLimit; reconfigure(TDM_SET_TIMING_GAINS);
     }
-    void PI4DQPSK::setOmegaGain(double omegaGain) { cfg.omega_gain = omegaGain; reconfigure(); }
-    void PI4DQPSK::setMuGain(double muGain) { cfg.mu_gain = muGain; reconfigure(); }
-    void PI4DQPSK::setOmegaRelLimit(double omegaRelLimit) { cfg.omega_rel_limit = omegaRelLimit; reconfigure(); }
+    void PI4DQPSK::setOmegaGain(double omegaGain) { cfg.omega_gain = omegaGain; reconfigure(TDM_SET_TIMING_GAINS); }
+    void PI4DQPSK::setMuGain(double muGain) { cfg.mu_gain = muGain; reconfigure(TDM_SET_TIMING_GAINS); }
+    void PI4DQPSK::setOmegaRelLimit(double omegaRelLimit) { cfg.omega_rel_limit = omegaRelLimit; reconfigure(TDM_SET_TIMING_GAINS); }
 
     void PI4DQPSK::reset() {
         assert(base_type::_block_init);

@@ -127,7 +127,7 @@ namespace dsp::b200 {
         }
 
     protected:
-        void reconfigure();
+        void reconfigure(uint32_t what);
         tdm_config cfg{};
         tdm_handle* handle = nullptr;
         int device = 0;

@@ -471,3 +471,55 @@ def test_full_scale_roundtrip_property(O, pkg, torch_cuda, n_channels, n_samples
             acc += (rr.dibits.to(torch.int64) * idx * valid).sum(dim=1)
             pos += rr.counts.to(torch.int64)
         assert torch.equal(acc, ref_sum)
+
+
+def test_setters_have_the_reference_effects(O, pkg, torch_cuda):
+    """PI4DQPSK's setters (src/dsp/pi4dqpsk.h:52-63) through tdm_set_params: each has the reference's own partial effect
+    (src/dsp/pi4dqpsk.cpp:31-118) -- in particular setSamplerate/setSymbolrate redesign the RRC taps and restart the
+    timing loop (COMPLEX_FD::setOmega) but never touch the band-edge filters.  Bit-exact against the checker's
+    restatement of that contract, and -- where the reference's own code is present -- against the reference driven
+    through its own setters (dibits identical once both have settled again)."""
+    torch = torch_cuda
+    C_, N1, N2 = 3, 30000, 60000
+    iq = O.generate(C_, N1 + N2)
+    a_part, b_part = np.ascontiguousarray(iq[:, :N1]), np.ascontiguousarray(iq[:, N1:])
+    cfg = pkg.default_config()
+    ocfg = O.OracleB.default_config()
+    ob = O.OracleB(C_)
+    ca1, _, da1, _ = ob.process(a_part)
+    steps = [("agc_rate", 0.01, pkg.capi.TDM_SET_AGC_RATE, 4), ("costas_bandwidth", 0.015, pkg.capi.TDM_SET_COSTAS_BW, 5),
+             ("fll_bandwidth", 0.004, pkg.capi.TDM_SET_FLL_BW, 6), ("samplerate", 36000.0, pkg.capi.TDM_SET_RATES, 2)]
+    with pkg.Demodulator(C_, N2) as dm:
+        r1 = dm.process(torch.from_numpy(a_part).cuda(), dibits=True)
+        torch.cuda.synchronize()
+        for field, value, what, _ in steps:
+            setattr(cfg, field, value)
+            setattr(ocfg, field, value)
+            dm.set_params(cfg, what)
+            ob.set_params(ocfg, what)
+        # setMMParams: gains and omega limits (complex_fd.cpp:44-61), loop state untouched
+        cfg.omega_gain, cfg.mu_gain, cfg.omega_rel_limit = cfg.omega_gain * 1.5, cfg.mu_gain * 1.5, 0.03
+        ocfg.omega_gain, ocfg.mu_gain, ocfg.omega_rel_limit = cfg.omega_gain, cfg.mu_gain, 0.03
+        dm.set_params(cfg, pkg.capi.TDM_SET_TIMING_GAINS)
+        ob.set_params(ocfg, 32)
+        d = dm.design()
+        assert abs(d.tr_max_omega - 2.06) < 1e-6                       # setOmegaRelLimit takes effect at once
+        st = dm.get_state()
+        assert (st["tr_offset"] == 0).all() and (st["tr_mu"] == 0).all() and (st["tr_omega"] == 2.0).all()   # setOmega's restart
+        res = dm.process(torch.from_numpy(b_part).cuda(), symbols=True, dibits=True)
+        cb, sb, db, _ = ob.process(b_part)
+        assert_matches_oracle_b(O, dm, ob, res, cb, sb, db)
+        got = res.dibits.cpu().numpy()
+    if O.have_ref():
+        oa = O.OracleA(C_)
+        oa.process(a_part, want_syms=False)
+        for _, value, _, code in steps:
+            oa.set(code, value)
+        oa.set(7, cfg.omega_gain, cfg.mu_gain, 0.03)
+        ca, _, da, _ = oa.process(b_part, want_syms=False)
+        for c in range(C_):
+            n = min(int(ca[c]), int(cb[c]))
+            assert abs(int(ca[c]) - int(cb[c])) <= 1
+            diff = np.flatnonzero(got[c, :n] != da[c, :n])
+            assert len(diff) == 0 or diff.max() < n // 2, f"channel {c}: differs from the reference's own setters at {diff[-5:]}"
+        oa.close()

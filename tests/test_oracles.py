@@ -211,3 +211,45 @@ def test_generator_mapping_is_bits2phase(O):
     d = O.tx_dibits(3, 40000)
     hist = np.bincount(d, minlength=4) / len(d)
     assert set(np.unique(d)) == {0, 1, 2, 3} and np.all(np.abs(hist - 0.25) < 0.02)
+
+
+def test_setter_contract_matches_the_reference(O):
+    """tdm_set_params' contract (restated in OracleB.set_params) against the reference driven through ITS OWN setters
+    (oracle/_ref, ref_driver.cpp tref_set): after the same sequence every loop coefficient, the timing restart and the
+    decoded dibits agree."""
+    if not O.have_ref():
+        pytest.skip("oracle/_ref not built here")
+    C_, N1, N2 = 3, 30000, 60000
+    iq = O.generate(C_, N1 + N2)
+    a, b = np.ascontiguousarray(iq[:, :N1]), np.ascontiguousarray(iq[:, N1:])
+    ob, oa, ocfg = O.OracleB(C_), O.OracleA(C_), O.OracleB.default_config()
+    ob.process(a)
+    oa.process(a, want_syms=False)
+    for field, value, what, code in [("agc_rate", 0.01, 4, 4), ("costas_bandwidth", 0.015, 8, 5), ("fll_bandwidth", 0.004, 16, 6),
+                                     ("samplerate", 36000.0, 1, 2)]:
+        setattr(ocfg, field, value)
+        ob.set_params(ocfg, what)
+        oa.set(code, value)
+    ocfg.omega_gain, ocfg.mu_gain, ocfg.omega_rel_limit = ocfg.omega_gain * 1.5, ocfg.mu_gain * 1.5, 0.03
+    ob.set_params(ocfg, 32)
+    oa.set(7, ocfg.omega_gain, ocfg.mu_gain, 0.03)
+    d = ob.design
+    got = np.array([0, d.fll_beta, d.fll_min_freq, d.fll_max_freq, d.tr_alpha, d.tr_beta, d.tr_min_omega, d.tr_max_omega, d.costas_alpha,
+                    d.costas_beta, d.costas_min_freq, d.costas_max_freq, d.agc_rate, d.agc_set_point, d.agc_max_gain, d.agc_init_gain], np.float32)
+    assert np.array_equal(got, oa.coeffs())
+    st = oa.loop_state(0)
+    assert (st.tr_mu, st.tr_omega, st.tr_offset) == (0.0, 2.0, 0) == (float(ob.states["tr_mu"][0]), float(ob.states["tr_omega"][0]), int(ob.states["tr_offset"][0]))
+    # an RRC redesign through setRRCParams leaves the band-edge filters alone in the reference; so does the contract
+    ocfg.rrc_beta = 0.5
+    ob.set_params(ocfg, 2)
+    oa.set(3, 65, 0.5)
+    nt, rrc, lbe, hbe, _, _, _ = oa.taps()
+    assert np.array_equal(np.array(ob.design.rrc[:], np.float32), rrc)
+    assert np.array_equal(np.array(ob.design.be_a[:], np.float32), hbe[:, 0]) and np.array_equal(np.array(ob.design.be_b[:], np.float32), hbe[:, 1])
+    cb, _, db, _ = ob.process(b)
+    ca, _, da, _ = oa.process(b, want_syms=False)
+    for c in range(C_):
+        n = min(int(ca[c]), int(cb[c]))
+        diff = np.flatnonzero(db[c, :n] != da[c, :n])
+        assert len(diff) == 0 or diff.max() < n // 2
+    oa.close()
