@@ -44,7 +44,13 @@ def test_threaded_block_chain_matches_oracle(O, tmp_path, buffer_samples, mode):
     if mode == "cycle":
         # reset() does not clear the slicer's previous-symbol memory or the delay lines' tails the way a fresh block
         # has them (src/dsp/pi4dqpsk.cpp:120-130): compare after the first run-in
-        assert len(got) == 2 * n, (len(got), 2 * n, r.stdout)
+        # the first run's buffer was left in the last stream when the chain was stopped and is delivered first after the
+        # restart (the streams are SDR++'s; the reference's chain would hand on its stale buffer the same way): 10000
+        # symbols of the first run, then the second run's stream
+        stale = 2 * (buffer_samples // 2)
+        assert len(got) == stale + 2 * n, (len(got), stale, 2 * n, r.stdout)
+        assert np.array_equal(got[:stale][4000:], bits[0, 4000:stale])
+        got = got[stale:]
         assert np.array_equal(got[4000:], bits[0, 4000:2 * n])
     else:
         assert len(got) == 2 * n, (len(got), 2 * n, r.stdout)
