@@ -424,11 +424,14 @@ def main():
         if world > 1:
             w = torch.arange(1, S + 1, device=dev, dtype=torch.int64) % 65521
 
-            def row_checksums(d, c):                          # position-weighted, 256 rows at a time (int64 temporaries)
+            def row_checksums(d, c):                          # position-weighted, 64 rows at a time (1 GB int64 temporaries)
                 parts = []
-                for r0 in range(0, d.shape[0], 256):
-                    v = torch.arange(S, device=dev)[None, :] < c[r0:r0 + 256][:, None]
-                    parts.append(((d[r0:r0 + 256, :S].to(torch.int64) * w[None, :]) * v).sum(dim=1))
+                for r0 in range(0, d.shape[0], 64):
+                    x = d[r0:r0 + 64, :S].to(torch.int64)
+                    x *= w[None, :]
+                    x *= torch.arange(S, device=dev)[None, :] < c[r0:r0 + 64][:, None]
+                    parts.append(x.sum(dim=1))
+                    del x
                 return torch.cat(parts)
 
             mysum = row_checksums(last.dibits, last.counts)

@@ -209,6 +209,24 @@ class OracleB:
             self.states["tr_omega"] = d.tr_init_omega
         self.cfg = cfg
 
+    def reset(self):
+        """tdm_reset's contract, restated: PI4DQPSK::reset() (src/dsp/pi4dqpsk.cpp:120-130) = FLL phase/frequency
+        (fll.cpp:120-127), the matched filter's delay line, the AGC gain, the Costas loop's phase/frequency and the
+        timing loop (complex_fd.cpp:78-87) back to their initial values; ph2, the slicer's memory, the lock metric
+        and the interpolator's history stay."""
+        st, d = self.states, self.design
+        st["fll_phase"] = 0
+        st["fll_freq"] = d.fll_init_freq
+        st["fll_quad"] = 0
+        st["fll_r"] = 0
+        st["x_hist"] = 0
+        st["agc_gain"] = d.agc_init_gain
+        st["costas_phase"] = 0
+        st["costas_freq"] = 0
+        st["tr_offset"] = 0
+        st["tr_mu"] = 0
+        st["tr_omega"] = d.tr_init_omega
+
     @staticmethod
     def default_config() -> TdmConfig:
         cfg = TdmConfig()
@@ -316,6 +334,11 @@ class OracleA:
         arr = (C.c_void_p * Cn)(*self.handles)
         self.L.tref_process_multi(arr, Cn, N, _ptr(iq), _ptr(dibits), S, _ptr(counts), nthreads)
         return counts, dibits
+
+    def reset(self):
+        """PI4DQPSK::reset() of every chain (src/dsp/pi4dqpsk.cpp:120-130)"""
+        for h in self.handles:
+            self.L.tref_reset(h)
 
     def set(self, what: int, a: float, b: float = 0.0, c: float = 0.0):
         """the reference's own setters on every chain (ref_driver.cpp tref_set: 1 setSymbolrate .. 10 setMuGain)"""

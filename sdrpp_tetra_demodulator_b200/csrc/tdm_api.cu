@@ -638,6 +638,7 @@ int tdm_reset(tdm_handle* h) {
     if (rc != TDM_OK) { return rc; }
     for (auto& s : st) {
         s.fll_phase = 0; s.fll_freq = h->design.fll_init_freq;
+        s.fll_quad = 0; s.fll_r = 0;            // the NCO's prepared reduction of phase 0 (tdm_math.cuh)
         std::memset(s.x_hist, 0, sizeof(s.x_hist));
         s.agc_gain = h->design.agc_init_gain;
         s.costas_phase = 0; s.costas_freq = 0;

@@ -217,6 +217,25 @@ def test_reference_shaped_classes(O, pkg, torch_cuda):
     assert not st["x_hist"].any()
 
 
+def test_reset_is_the_checkers_reset(O, pkg, torch_cuda):
+    """tdm_reset (PI4DQPSK::reset(), src/dsp/pi4dqpsk.cpp:120-130) in the middle of a capture: what is restarted and what
+    is kept follows the contract OracleB.reset() restates (tests/test_oracles.py pins that against the reference's own
+    reset), so the next call is bit-exact again -- including the NCO's prepared reduction, which has to restart with the
+    phase."""
+    torch = torch_cuda
+    C_, N = 4, 30000
+    iq = O.generate(C_, N)
+    ob = O.OracleB(C_)
+    ob.process(iq[:, :11111])
+    ob.reset()
+    cb, sb, db, _ = ob.process(iq)
+    with pkg.Demodulator(C_, N) as dm:
+        dm.process(torch.from_numpy(np.ascontiguousarray(iq[:, :11111])).cuda(), dibits=True)
+        dm.reset()
+        res = dm.process(torch.from_numpy(iq).cuda(), symbols=True, dibits=True)
+        assert_matches_oracle_b(O, dm, ob, res, cb, sb, db)
+
+
 def test_checkpoint_resume(O, pkg, torch_cuda):
     """tdm_get_state / tdm_set_state: stop after any chunk, resume in a new handle, same output."""
     torch = torch_cuda

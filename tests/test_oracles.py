@@ -253,3 +253,30 @@ def test_setter_contract_matches_the_reference(O):
         diff = np.flatnonzero(db[c, :n] != da[c, :n])
         assert len(diff) == 0 or diff.max() < n // 2
     oa.close()
+
+
+def test_reset_contract_matches_the_reference(O):
+    """tdm_reset's contract (restated in OracleB.reset) against the reference's own PI4DQPSK::reset()
+    (src/dsp/pi4dqpsk.cpp:120-130): loops restart from their initial values, both acquire again and the decoded dibits
+    agree from the reference's lock point on.  (The reference keeps the band-edge filters' delay line across a reset
+    and clears the matched filter's; the product has ONE delay line for both and clears it -- a 64-sample transient,
+    before either has locked.)"""
+    if not O.have_ref():
+        pytest.skip("oracle/_ref not built here")
+    C_, N = 8, 60000
+    iq = O.generate(C_, N)
+    oa, ob = O.OracleA(C_), O.OracleB(C_)
+    oa.process(iq[:, :20000], want_syms=False)
+    ob.process(iq[:, :20000])
+    oa.reset()
+    ob.reset()
+    st = oa.loop_state(0)
+    assert (st.tr_mu, st.tr_omega, st.tr_offset) == (0.0, 2.0, 0)
+    assert float(ob.states["agc_gain"][0]) == 1.0 and float(ob.states["fll_phase"][0]) == 0.0
+    ca, _, da, _ = oa.process(iq, want_syms=False)
+    cb, _, db, _ = ob.process(iq)
+    for c in range(C_):
+        assert ca[c] == cb[c]
+        diff = np.flatnonzero(da[c, :ca[c]] != db[c, :ca[c]])
+        assert len(diff) == 0 or diff.max() < ca[c] // 2, (c, diff[-5:])      # slowest channel of this capture locks near 9100
+    oa.close()
