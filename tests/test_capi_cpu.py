@@ -153,3 +153,47 @@ def test_headers_are_plain_c_and_the_example_fails_loudly_without_a_gpu(pkg, tmp
         return
     r = subprocess.run([str(exe)], capture_output=True, text=True)
     assert r.returncode == 3 and "no CPU fallback" in r.stderr, (r.returncode, r.stderr)
+
+
+def _build_sharded_gather(pkg, tmp_path):
+    import subprocess
+    exe = tmp_path / "sharded_gather"
+    libdir = os.path.dirname(pkg.capi.LIB_PATH)
+    cuda = os.environ.get("CUDA_HOME", "/usr/local/cuda")
+    r = subprocess.run(["gcc", "-std=c11", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", os.path.join(ROOT, "include"), "-I", os.path.join(cuda, "include"),
+                        os.path.join(ROOT, "examples", "sharded_gather.c"), "-L", libdir, "-ltdm_b200", "-L", os.path.join(cuda, "lib64"), "-lcudart",
+                        f"-Wl,-rpath,{libdir}", f"-Wl,-rpath,{os.path.join(cuda, 'lib64')}", "-o", str(exe)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    return exe
+
+
+def test_multi_gpu_example_builds_and_fails_loudly_without_a_gpu(pkg, tmp_path):
+    """examples/sharded_gather.c: the multi-GPU epilogue (tdm_comm_*, tdm_gather_packed, tdm_unpack_dibits) from plain C"""
+    import shutil
+    import subprocess
+    import torch
+    if not shutil.which("gcc") or not os.path.exists("/usr/local/cuda/include/cuda_runtime_api.h"):
+        pytest.skip("gcc or the CUDA headers are missing")
+    exe = _build_sharded_gather(pkg, tmp_path)
+    if torch.cuda.is_available():
+        return
+    r = subprocess.run([str(exe), "0", "1", str(tmp_path / "id")], capture_output=True, text=True)
+    assert r.returncode == 3 and "no CPU fallback" in r.stderr, (r.returncode, r.stderr)
+
+
+@pytest.mark.gpu
+def test_multi_gpu_example_runs(pkg, tmp_path):
+    """one rank per visible GPU (two at most): every rank demodulates its shard, rank 0 receives all rows over NCCL and its
+    own channels equal the transmitted dibits after lock"""
+    import subprocess
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    exe = _build_sharded_gather(pkg, tmp_path)
+    world = min(2, torch.cuda.device_count())
+    procs = [subprocess.Popen([str(exe), str(r), str(world), str(tmp_path / "id"), "64", "60000"], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+             for r in range(world)]
+    outs = [p.communicate(timeout=300) for p in procs]
+    for p, (o, e) in zip(procs, outs):
+        assert p.returncode == 0, (o, e)
+    assert f"rank 0 holds {64 * world} channels" in outs[0][0] and " 0 of its own 64 channels differ" in outs[0][0], outs[0][0]
