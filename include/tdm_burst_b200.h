@@ -91,7 +91,8 @@ typedef struct tdm_bsync tdm_bsync;
 
 /* n_channels independent tetra_rx_state objects, zero-initialised like the reference's
  * talloc_zero (src/dsp/osmotetra_dec.h).  max_units = most input bytes per channel a
- * later tdm_bsync_in passes. */
+ * later tdm_bsync_in passes.  At most 65535 channels per handle (TDM_ERR_UNSUPPORTED
+ * above; same limit per call of tdm_find_train_seq). */
 int tdm_bsync_create(int32_t n_channels, int64_t max_units, int32_t device, tdm_bsync** out);
 int tdm_bsync_destroy(tdm_bsync* h);
 /* cudaStream_t as void*; NULL = legacy default stream, TDM_OWN_STREAM = the handle's own. */

@@ -724,6 +724,7 @@ int tdm_bsync_create(int32_t n_channels, int64_t max_units, int32_t device, tdm_
     if (!out) { return tdm_internal_fail(TDM_ERR_ARG, "tdm_bsync_create: out is null"); }
     *out = nullptr;
     if (n_channels <= 0 || max_units <= 0 || max_units > (1LL << 29)) { return tdm_internal_fail(TDM_ERR_ARG, "tdm_bsync_create: n_channels and max_units must be > 0 (max_units <= 2^29)"); }
+    if (n_channels > 65535) { return tdm_internal_fail(TDM_ERR_UNSUPPORTED, "tdm_bsync_create: at most 65535 channels per handle (one grid row per channel); use several handles"); }
     int rc = check_device("tdm_bsync_create", device);
     if (rc != TDM_OK) { return rc; }
     tdm_bsync* h = new (std::nothrow) tdm_bsync();
@@ -901,6 +902,7 @@ int tdm_find_train_seq(int32_t device, void* cuda_stream, const uint8_t* in, int
     const long long wstride = words_for(end_of_in);
     uint32_t* d_wb = nullptr;
     uint8_t* d_in = nullptr;
+    if (n_channels > 65535) { return tdm_internal_fail(TDM_ERR_UNSUPPORTED, "tdm_find_train_seq: at most 65535 channels per call (one grid row per channel)"); }
     int* d_type = nullptr;
     uint32_t* d_off = nullptr;
     auto done = [&](int code) { cudaFree(d_wb); cudaFree(d_in); cudaFree(d_type); cudaFree(d_off); return code; };

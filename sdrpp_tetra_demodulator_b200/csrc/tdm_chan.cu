@@ -75,7 +75,7 @@ __global__ void __launch_bounds__(256) chan_polyphase_kernel(const float2* __res
     float h[T];
 #pragma unroll
     for (int q = 0; q < T; ++q) { h[q] = __ldg(taps + p + (long long)q * M); }
-    const long long m0 = (long long)blockIdx.y * kTile;
+  for (long long m0 = (long long)blockIdx.y * kTile; m0 < n_out; m0 += (long long)gridDim.y * kTile) {      // grid.y is capped at 65535
     for (int i = 0; i < kTile; ++i) {
         const long long m = m0 + i;
         if (m >= n_out) { break; }
@@ -93,6 +93,7 @@ __global__ void __launch_bounds__(256) chan_polyphase_kernel(const float2* __res
         if (pp < 0) { pp += M; }
         u[m * M + pp] = acc;
     }
+  }
 }
 
 // the last n_hist samples of [hist | in] become the new history
@@ -247,7 +248,8 @@ int tdm_chan_process(tdm_chan* c, const float* wide, int64_t n_wide, float* out,
         c->plan_batch = n_out; c->plan_stride = out_stride;
     }
     const float2* in = reinterpret_cast<const float2*>(wide);
-    dim3 grid((unsigned)((M + 255) / 256), (unsigned)((n_out + kTile - 1) / kTile));
+    const long long n_tiles = (n_out + kTile - 1) / kTile;
+    dim3 grid((unsigned)((M + 255) / 256), (unsigned)(n_tiles < 65535 ? n_tiles : 65535));
     cudaEventRecord(c->ev[0], st);
 #define TDM_CHAN_LAUNCH(TT) chan_polyphase_kernel<TT><<<grid, 256, 0, st>>>(in, c->d_hist[c->cur], c->n_hist, c->d_taps, M, D, n_out, c->t_global, c->d_u)
     switch (T) {

@@ -163,24 +163,25 @@ __global__ void stitch_adopt_kernel(uint8_t* __restrict__ dib, long long stride,
                                     int* __restrict__ counts, const int* __restrict__ counts2, int* __restrict__ join, int* __restrict__ fixed,
                                     const int* __restrict__ mode, tdm_channel_state* __restrict__ final_states,
                                     const tdm_channel_state* __restrict__ run_states, int* __restrict__ cut, int n_rows) {
-    const int c = blockIdx.y;
-    if (mode[c] != 1) { return; }
-    const int len = counts2[c];
-    const uint8_t* __restrict__ src = dib2 + (long long)c * stride2;
-    uint8_t* __restrict__ dst = dib + (long long)c * stride;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < len; i += gridDim.x * blockDim.x) { dst[i] = src[i]; }
-    if (blockIdx.x == 0) {
-        for (int k = threadIdx.x; k < kStateWords; k += blockDim.x) {
-            reinterpret_cast<uint32_t*>(final_states + c)[k] = reinterpret_cast<const uint32_t*>(run_states + c)[k];
+    for (int c = blockIdx.y; c < n_rows; c += gridDim.y) {             // grid.y is capped at 65535; c is uniform in a block
+        if (mode[c] != 1) { continue; }
+        const int len = counts2[c];
+        const uint8_t* __restrict__ src = dib2 + (long long)c * stride2;
+        uint8_t* __restrict__ dst = dib + (long long)c * stride;
+        for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < len; i += gridDim.x * blockDim.x) { dst[i] = src[i]; }
+        if (blockIdx.x == 0) {
+            for (int k = threadIdx.x; k < kStateWords; k += blockDim.x) {
+                reinterpret_cast<uint32_t*>(final_states + c)[k] = reinterpret_cast<const uint32_t*>(run_states + c)[k];
+            }
         }
-    }
-    __syncthreads();
-    if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) {
-        counts[c] = len; join[c] = 0; fixed[c] = 1;
-        // a successor that joined this row's EXTENDED old stream late has to look again: that stream is gone
-        if (cut[c] > 0) {
-            cut[c] = 0;
-            if (c + 1 < n_rows && fixed[c + 1] == 3) { fixed[c + 1] = 0; join[c + 1] = -1; }
+        __syncthreads();
+        if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) {
+            counts[c] = len; join[c] = 0; fixed[c] = 1;
+            // a successor that joined this row's EXTENDED old stream late has to look again: that stream is gone
+            if (cut[c] > 0) {
+                cut[c] = 0;
+                if (c + 1 < n_rows && fixed[c + 1] == 3) { fixed[c + 1] = 0; join[c + 1] = -1; }
+            }
         }
     }
 }
@@ -202,29 +203,32 @@ __global__ void stitch_scan_kernel(const int* __restrict__ counts, const int* __
 }
 
 __global__ void stitch_copy_kernel(const uint8_t* __restrict__ dib, long long stride, const int* __restrict__ counts, const int* __restrict__ cut,
-                                   const int* __restrict__ join, const long long* __restrict__ offs, int S, uint8_t* __restrict__ out, long long out_stride) {
-    const int r = blockIdx.y;
-    const int skip = (r % S == 0) ? 0 : join[r];
-    if (skip < 0) { return; }
-    const uint8_t* __restrict__ src = dib + (long long)r * stride + skip;
-    const int len = (cut[r] > 0 ? cut[r] : counts[r]) - skip;
-    const long long o = offs[r];
-    uint8_t* __restrict__ dst = out + (long long)(r / S) * out_stride;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < len; i += gridDim.x * blockDim.x) {
-        if (o + i < out_stride) { dst[o + i] = src[i]; }
+                                   const int* __restrict__ join, const long long* __restrict__ offs, int S, uint8_t* __restrict__ out, long long out_stride,
+                                   int n_rows) {
+    for (int r = blockIdx.y; r < n_rows; r += gridDim.y) {             // grid.y is capped at 65535
+        const int skip = (r % S == 0) ? 0 : join[r];
+        if (skip < 0) { continue; }
+        const uint8_t* __restrict__ src = dib + (long long)r * stride + skip;
+        const int len = (cut[r] > 0 ? cut[r] : counts[r]) - skip;
+        const long long o = offs[r];
+        uint8_t* __restrict__ dst = out + (long long)(r / S) * out_stride;
+        for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < len; i += gridDim.x * blockDim.x) {
+            if (o + i < out_stride) { dst[o + i] = src[i]; }
+        }
     }
 }
 
 // append the tail run of every channel (row c of `src`, count[c] dibits) behind what the segments produced
 __global__ void stitch_append_kernel(const uint8_t* __restrict__ src, long long stride, const int* __restrict__ count, long long* __restrict__ totals,
-                                     uint8_t* __restrict__ out, long long out_stride) {
-    const int c = blockIdx.y;
-    const long long o = totals[c];
-    const int len = count[c];
-    const uint8_t* __restrict__ s = src + (long long)c * stride;
-    uint8_t* __restrict__ dst = out + (long long)c * out_stride;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < len; i += gridDim.x * blockDim.x) {
-        if (o + i < out_stride) { dst[o + i] = s[i]; }
+                                     uint8_t* __restrict__ out, long long out_stride, int C) {
+    for (int c = blockIdx.y; c < C; c += gridDim.y) {
+        const long long o = totals[c];
+        const int len = count[c];
+        const uint8_t* __restrict__ s = src + (long long)c * stride;
+        uint8_t* __restrict__ dst = out + (long long)c * out_stride;
+        for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < len; i += gridDim.x * blockDim.x) {
+            if (o + i < out_stride) { dst[o + i] = s[i]; }
+        }
     }
 }
 __global__ void stitch_bump_kernel(const int* __restrict__ count, long long* __restrict__ totals, int C) {
@@ -265,7 +269,7 @@ void launch_stitch_adopt(uint8_t* dib, long long stride, const uint8_t* dib2, lo
                          cudaStream_t s) {
     stitch_verify_kernel<<<(n_rows + 3) / 4, 128, 0, s>>>(dib, stride, dib2, stride2, counts, counts2, adopt, n_rows, K, agree);
     stitch_decide_kernel<<<1, 32, 0, s>>>(join, fixed, counts, adopt, agree, n_rows, S, force_at, mode, n_forced);
-    stitch_adopt_kernel<<<dim3(blocks_for(max_len, 256, 256), (unsigned)n_rows), 256, 0, s>>>(dib, stride, dib2, stride2, counts, counts2, join, fixed,
+    stitch_adopt_kernel<<<dim3(blocks_for(max_len, 256, 256), (unsigned)(n_rows < 65535 ? n_rows : 65535)), 256, 0, s>>>(dib, stride, dib2, stride2, counts, counts2, join, fixed,
                                                                                               mode, final_states, run_states, cut, n_rows);
 }
 void launch_stitch_scan(const int* counts, const int* cut, const int* join, int n_rows, int S, long long* offs, long long* totals, cudaStream_t s) {
@@ -274,11 +278,11 @@ void launch_stitch_scan(const int* counts, const int* cut, const int* join, int 
 }
 void launch_stitch_copy(const uint8_t* dib, long long stride, const int* counts, const int* cut, const int* join, const long long* offs, int S,
                         uint8_t* out, long long out_stride, int n_rows, long long max_len, cudaStream_t s) {
-    stitch_copy_kernel<<<dim3(blocks_for(max_len, 256, 512), (unsigned)n_rows), 256, 0, s>>>(dib, stride, counts, cut, join, offs, S, out, out_stride);
+    stitch_copy_kernel<<<dim3(blocks_for(max_len, 256, 512), (unsigned)(n_rows < 65535 ? n_rows : 65535)), 256, 0, s>>>(dib, stride, counts, cut, join, offs, S, out, out_stride, n_rows);
 }
 void launch_stitch_append(const uint8_t* src, long long stride, const int* count, long long* totals, uint8_t* out, long long out_stride, int C,
                           long long max_len, cudaStream_t s) {
-    stitch_append_kernel<<<dim3(blocks_for(max_len, 256, 64), (unsigned)C), 256, 0, s>>>(src, stride, count, totals, out, out_stride);
+    stitch_append_kernel<<<dim3(blocks_for(max_len, 256, 64), (unsigned)(C < 65535 ? C : 65535)), 256, 0, s>>>(src, stride, count, totals, out, out_stride, C);
     stitch_bump_kernel<<<(C + 127) / 128, 128, 0, s>>>(count, totals, C);
 }
 

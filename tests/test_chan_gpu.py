@@ -88,3 +88,22 @@ def test_wideband_to_dibits_end_to_end(O, pkg, torch_cuda):
         assert len(errs[lag]) == 0, f"carrier on channel {c}: {len(errs[lag])} dibit errors after symbol {first} (lag {lag}), at {errs[lag][:8] + first}"
         assert sync[c] == 1
     assert sync[[20, 50, 120]].sum() == 0          # empty channels do not report lock
+
+
+def test_more_instants_than_a_grid_dimension(pkg, torch_cuda):
+    """1.1 million output instants in one call (16 per block, a grid's y dimension ends at 65 535): the same samples as the
+    stream cut in two calls."""
+    torch = torch_cuda
+    cfg = pkg.chan_default_config(1)             # M = 36, D = 25
+    D, n_out = cfg.decimation, 1_100_000
+    g = torch.Generator(device="cuda").manual_seed(5)
+    wide = torch.randn((n_out * D, 2), generator=g, device="cuda", dtype=torch.float32)
+    with pkg.Channelizer(cfg) as ch:
+        whole = ch.process(wide)
+        ch.reset()
+        cut = 600_000 * D
+        a = ch.process(wide[:cut].contiguous())
+        b = ch.process(wide[cut:].contiguous())
+        torch.cuda.synchronize()
+        assert torch.equal(whole[:, :600_000], a) and torch.equal(whole[:, 600_000:], b)
+        assert float(whole[:, -1000:].abs().max()) > 0

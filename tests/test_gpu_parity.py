@@ -542,3 +542,32 @@ def test_setters_have_the_reference_effects(O, pkg, torch_cuda):
             diff = np.flatnonzero(got[c, :n] != da[c, :n])
             assert len(diff) == 0 or diff.max() < n // 2, f"channel {c}: differs from the reference's own setters at {diff[-5:]}"
         oa.close()
+
+
+def test_more_rows_than_a_grid_dimension(O, pkg, torch_cuda):
+    """66 000 rows in one handle (a CUDA grid's y dimension ends at 65 535): the demodulator, the packed output, tdm_pack_dibits
+    and tdm_unpack_dibits walk rows in loops.  64 distinct channels repeated; every replica must equal its original, and
+    the originals the checker."""
+    torch = torch_cuda
+    C0, R, N = 64, 1032, 4096
+    C_ = C0 * R                                     # 66 048
+    iq0 = O.generate(C0, N)
+    ob = O.OracleB(C0)
+    cb, _, db, _ = ob.process(iq0)
+    iq = torch.from_numpy(iq0).cuda().repeat(R, 1, 1).contiguous()
+    with pkg.Demodulator(C_, N) as dm:
+        res = dm.process(iq, dibits=True, packed=True)
+        torch.cuda.synchronize()
+        counts = res.counts.view(R, C0)
+        assert torch.equal(counts, counts[0:1].expand(R, C0)) and np.array_equal(counts[0].cpu().numpy(), cb)
+        S = int(cb.max())
+        d = res.dibits[:, :S].view(R, C0, S)
+        valid = (torch.arange(S, device=d.device)[None, :] < counts[0][:, None].to(torch.int64))[None]
+        assert bool(((d == d[0:1]) | ~valid).all())
+        first = d[0].cpu().numpy()
+        for c in range(C0):
+            assert np.array_equal(first[c, :cb[c]], db[c, :cb[c]])
+        ud, _ = dm.unpack_dibits(res.packed, res.counts, max_symbols=S, dibits=True)
+        assert bool(((ud[:, :S].view(R, C0, S) == d) | ~valid).all())
+    with pytest.raises(Exception):
+        pkg.BurstSync(70000, 1024)                  # one grid row per channel there: refused, not mis-launched
