@@ -123,14 +123,17 @@ def cpu_reference_throughput(seconds_hint: float = 15.0):
     base = O.generate(min(n_ch, 8), 100_000)
     iq = np.ascontiguousarray(np.tile(base, (-(-n_ch // base.shape[0]), n_s // base.shape[1], 1))[:n_ch])
     if O.have_ref():
-        a = O.OracleA(n_ch)
+        simd = O.have_ref_simd()              # the build whose VOLK stand-in has 256-bit FMA dot products, where the host can run it
+        a = O.OracleA(n_ch, simd=simd)
         a.process_multi(iq, cores)            # untimed pass: first touch of the blocks' 8 MB work buffers
         t0 = time.perf_counter()
         counts, _ = a.process_multi(iq, cores)
         dt = time.perf_counter() - t0
         a.close()
         kind = "reference"
-        what = "reference src/dsp/*.cpp (oracle/_ref, scalar VOLK stand-in: no SIMD dot products, g++ -O3 -ffp-contract=off, no -march=native)"
+        what = ("reference src/dsp/*.cpp (oracle/_ref/libtetra_ref_simd.so: g++ -O3 -mavx2 -mfma, the VOLK stand-in's dot products as 256-bit FMA "
+                "kernels like the ones VOLK dispatches to on this host; same decoded dibits as the generic-order build)" if simd else
+                "reference src/dsp/*.cpp (oracle/_ref, scalar VOLK stand-in: this host has no AVX2+FMA or the SIMD build is missing; g++ -O3 -ffp-contract=off)")
     else:
         b = O.OracleB(n_ch)
         b.process(iq, want_syms=False, nthreads=cores)

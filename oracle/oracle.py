@@ -18,6 +18,7 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 REF_SO = os.path.join(HERE, "_ref", "libtetra_ref.so")
 REF_SO_REONLY = os.path.join(HERE, "_ref", "libtetra_ref_reonly.so")   # fastAmplitude() with both operands from |re|
+REF_SO_SIMD = os.path.join(HERE, "_ref", "libtetra_ref_simd.so")       # AVX2+FMA dot products in the VOLK stand-in: timing only
 TDM_CFG_FASTAMP_RE_ONLY = 1
 
 TDM_MAX_TAPS = 65
@@ -261,13 +262,23 @@ def have_ref(fastamp_re_only: bool = False) -> bool:
     return os.path.exists(REF_SO_REONLY if fastamp_re_only else REF_SO)
 
 
+def have_ref_simd() -> bool:
+    """the timing build of the reference (VOLK stand-in with 256-bit FMA kernels) and a host that can run it"""
+    try:
+        with open("/proc/cpuinfo") as f:
+            flags = next((line for line in f if line.startswith("flags")), "")
+    except OSError:
+        flags = ""
+    return os.path.exists(REF_SO_SIMD) and " avx2 " in flags + " " and " fma " in flags + " "
+
+
 _LIB_A = {}
 
 
-def lib_a(fastamp_re_only: bool = False) -> C.CDLL:
-    key = bool(fastamp_re_only)
+def lib_a(fastamp_re_only: bool = False, simd: bool = False) -> C.CDLL:
+    key = "simd" if simd else bool(fastamp_re_only)
     if key not in _LIB_A:
-        path = REF_SO_REONLY if key else REF_SO
+        path = REF_SO_SIMD if simd else (REF_SO_REONLY if fastamp_re_only else REF_SO)
         if not os.path.exists(path):
             raise FileNotFoundError(f"{path} missing: run `make -C oracle ref` where /root/reference exists")
         L = C.CDLL(path)
@@ -293,8 +304,8 @@ def lib_a(fastamp_re_only: bool = False) -> C.CDLL:
 class OracleA:
     """The reference's own PI4DQPSK -> DQPSKSymbolExtractor -> BitUnpacker chain, one instance per channel."""
 
-    def __init__(self, n_channels: int = 1, params: TrefParams | None = None, fastamp_re_only: bool = False):
-        self.L = lib_a(fastamp_re_only)
+    def __init__(self, n_channels: int = 1, params: TrefParams | None = None, fastamp_re_only: bool = False, simd: bool = False):
+        self.L = lib_a(fastamp_re_only, simd)
         self.n_channels = n_channels
         self.handles = [self.L.tref_create(C.byref(params) if params is not None else None)
                         for _ in range(n_channels)]

@@ -280,3 +280,17 @@ def test_reset_contract_matches_the_reference(O):
         diff = np.flatnonzero(da[c, :ca[c]] != db[c, :ca[c]])
         assert len(diff) == 0 or diff.max() < ca[c] // 2, (c, diff[-5:])      # slowest channel of this capture locks near 9100
     oa.close()
+
+
+def test_simd_timing_build_of_the_reference_decodes_the_same_dibits(O):
+    """oracle/_ref/libtetra_ref_simd.so -- the reference with 256-bit FMA dot products in the VOLK stand-in, the build
+    bench.py TIMES as the CPU baseline -- against the generic-order build that pins parity: same symbol counts, same
+    dibits from the lock point on (the floats differ in the last places, as real VOLK's do between machines)."""
+    if not O.have_ref() or not O.have_ref_simd():
+        pytest.skip("oracle/_ref SIMD build not present or host without AVX2+FMA")
+    g = golden_case("batch_c8_n60000_snr30")
+    a = O.OracleA(g.n_channels, simd=True)
+    counts, _, dibits, _ = a.process(g.iq, want_syms=False)
+    for c in range(g.n_channels):
+        g.assert_dibits_match(c, dibits[c], counts[c])
+    a.close()
