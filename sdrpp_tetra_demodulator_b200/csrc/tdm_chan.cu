@@ -61,39 +61,91 @@ double bessel_i0(double x) {
     return s;
 }
 
-// Branch sums of a tile of output instants.  grid = (ceil(M / 256), ceil(n_out / kTile)), block = 256: thread = branch p,
-// looping over the tile's instants; the prototype taps of the branch (T values) live in registers for the whole tile.
-// x(i): i < 0 reads the carried history (the last T M samples of the previous calls), i >= 0 the new samples.
-// Loads are coalesced: consecutive branches read consecutive wideband samples (descending), stores likewise (rotated).
-constexpr int kTile = 16;
+// Branch sums, organised by RESIDUE.  Branch sum v_m[p] reads the samples t_m - p - q M, q < T: all in the residue class
+// rho = (t_m - p) mod M.  Seen from a residue class, the filterbank is an ordinary T-tap FIR over the class's own
+// samples x_rho[j] = x[rho + j M] whose tap set changes with the instant (p_m = (t_m - rho) mod M), and consecutive
+// instants reuse all but D/M of a sample on average.  So a CTA takes a slab of 32 residue classes and a chunk of
+// instants, stages the slab's sample window in shared memory ONCE (rows of 32 consecutive wideband samples: 256-byte
+// coalesced reads, each sample of the capture read by exactly one slab), and its threads (lane = residue class, warp =
+// instant lane) form the branch sums from shared memory; the taps come through L1 (CTAs that run together share the
+// slab, grid.x = chunk).  The first version had thread = branch and re-read every sample T M / D = 23 times from L2
+// (1.39 ms per 16384 instants of 4608 channels, L2-bandwidth bound).  Sums run q = 0 .. T-1 as before: same bits.
+constexpr int kSlab = 32;
+constexpr int kChanRows = 192;               // rows of the staged window: 192 x 256 B = 48 KB
+__device__ __forceinline__ long long floor_div(long long a, long long b) { return a >= 0 ? a / b : -((-a + b - 1) / b); }
 template <int T>
-__global__ void __launch_bounds__(256) chan_polyphase_kernel(const float2* __restrict__ in, const float2* __restrict__ hist, long long n_hist,
-                                                             const float* __restrict__ taps, int M, int D, long long n_out,
-                                                             long long t0_global /* global index of in[0] */, float2* __restrict__ u) {
-    const int p = blockIdx.x * 256 + threadIdx.x;
-    if (p >= M) { return; }
-    float h[T];
-#pragma unroll
-    for (int q = 0; q < T; ++q) { h[q] = __ldg(taps + p + (long long)q * M); }
-  for (long long m0 = (long long)blockIdx.y * kTile; m0 < n_out; m0 += (long long)gridDim.y * kTile) {      // grid.y is capped at 65535
-    for (int i = 0; i < kTile; ++i) {
-        const long long m = m0 + i;
-        if (m >= n_out) { break; }
-        const long long tl = (m + 1) * D - 1;                 // newest sample of this instant, local index
+__global__ void __launch_bounds__(256) chan_residue_kernel(const float2* __restrict__ in, long long n_in, const float2* __restrict__ hist, long long n_hist,
+                                                           const float* __restrict__ taps, int M, int D, long long n_out, int mi,
+                                                           long long t0_global /* global index of in[0] */, float2* __restrict__ u) {
+    __shared__ float2 xs[kChanRows * kSlab];
+    const int lane = threadIdx.x & 31, il = threadIdx.x >> 5;
+    const int rho0 = blockIdx.y * kSlab, rho = rho0 + lane;
+    const long long m0 = (long long)blockIdx.x * mi;
+    const int cnt = (int)((n_out - m0) < mi ? (n_out - m0) : mi);
+    // t_m - rho = base + (m - m0) D + (31 - lane) with base = t_{m0} - rho0 - 31; J = floor((t_m - rho) / M) = Jb + a / M, p = a % M,
+    // a = rem + (m - m0) D + 31 - lane (32-bit: mi D < 2^30)
+    const long long base = (m0 + 1) * D - 1 - rho0 - (kSlab - 1);
+    const long long Jb = floor_div(base, M);
+    const int rem = (int)(base - Jb * M);
+    const long long Jlo = Jb - (T - 1);                                      // first staged row
+    const int rows = (int)((rem + (long long)(cnt - 1) * D + (kSlab - 1)) / M) + T;      // <= kChanRows by the host's choice of mi
+    if (rho < M) {
+        for (int r = il; r < rows; r += 8) {
+            const long long idx = (long long)rho + (Jlo + r) * M;            // local sample index: >= 0 new samples, < 0 carried history
+            float2 v = make_float2(0.f, 0.f);
+            if (idx >= 0) { if (idx < n_in) { v = __ldg(in + idx); } }
+            else if (n_hist + idx >= 0) { v = hist[n_hist + idx]; }
+            xs[r * kSlab + lane] = v;
+        }
+    }
+    __syncthreads();
+    if (rho >= M) { return; }
+    // this thread's instants: m0 + il, m0 + il + 8, ...  (a, rotation) advance by 8 D per step, reduced without divisions
+    const int stepq = (int)((8LL * D) / M), stepr = (int)((8LL * D) % M);
+    const unsigned a0 = (unsigned)rem + (unsigned)il * (unsigned)D + (unsigned)(kSlab - 1 - lane);
+    int jr = (int)(a0 / (unsigned)M) + (T - 1);                               // row of the newest sample (q = 0)
+    int pbr = (int)(a0 % (unsigned)M);                                        // branch
+    int rot = (int)((t0_global + (m0 + il + 1) * D - 1) % M);                 // r_m
+    for (int k = il; k < cnt; k += 8) {
         float2 acc = make_float2(0.f, 0.f);
 #pragma unroll
         for (int q = 0; q < T; ++q) {
-            const long long idx = tl - p - (long long)q * M;
-            const float2 x = idx >= 0 ? __ldg(in + idx) : hist[n_hist + idx];
-            acc.x = fmaf(h[q], x.x, acc.x);
-            acc.y = fmaf(h[q], x.y, acc.y);
+            const float h = __ldg(taps + pbr + (long long)q * M);
+            const float2 x = xs[(jr - q) * kSlab + lane];
+            acc.x = fmaf(h, x.x, acc.x);
+            acc.y = fmaf(h, x.y, acc.y);
         }
-        const int r = (int)((t0_global + tl) % M);
-        int pp = p - r;
+        int pp = pbr - rot;
         if (pp < 0) { pp += M; }
-        u[m * M + pp] = acc;
+        u[(m0 + k) * M + pp] = acc;
+        pbr += stepr; jr += stepq;
+        if (pbr >= M) { pbr -= M; ++jr; }
+        rot += stepr;
+        if (rot >= M) { rot -= M; }
     }
-  }
+}
+
+// [n_out][M] (what the batched DFT leaves, instant-major) -> [M][out_stride] (channel-major rows the demodulator reads in place)
+__global__ void __launch_bounds__(256) chan_transpose_kernel(const float2* __restrict__ v, float2* __restrict__ out, int M, long long n_out, long long out_stride) {
+    __shared__ float2 tile[32][33];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const long long m0 = (long long)blockIdx.x * 32;
+    for (int k0 = blockIdx.y * 32; k0 < M; k0 += gridDim.y * 32) {
+#pragma unroll
+        for (int i = ty; i < 32; i += 8) {
+            const long long m = m0 + i;
+            const int k = k0 + tx;
+            if (m < n_out && k < M) { tile[i][tx] = v[m * M + k]; }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int i = ty; i < 32; i += 8) {
+            const int k = k0 + i;
+            const long long m = m0 + tx;
+            if (m < n_out && k < M) { out[(long long)k * out_stride + m] = tile[tx][i]; }
+        }
+        __syncthreads();
+    }
 }
 
 // the last n_hist samples of [hist | in] become the new history
@@ -240,18 +292,22 @@ int tdm_chan_process(tdm_chan* c, const float* wide, int64_t n_wide, float* out,
     if (!c->plan || c->plan_batch != n_out || c->plan_stride != out_stride) {
         if (c->plan) { cufft().Destroy(c->plan); c->plan = 0; }
         int n[1] = { M }, inembed[1] = { M }, onembed[1] = { M };
-        // input: instant m at u + m M, unit stride; output: channel k of instant m at out + k * out_stride + m
-        if (out_stride > 0x7fffffffLL || cufft().PlanMany(&c->plan, 1, n, inembed, 1, M, onembed, (int)out_stride, 1, CUFFT_C2C_, (int)n_out) != 0) {
+        // instant m at u + m M, unit stride, in place; chan_transpose_kernel then writes channel k of instant m at out + k * out_stride + m
+        // (cuFFT can write that layout itself -- ostride = out_stride, odist = 1 -- but took 0.89 ms for 16384 x 4608 that way)
+        if (cufft().PlanMany(&c->plan, 1, n, inembed, 1, M, onembed, 1, M, CUFFT_C2C_, (int)n_out) != 0) {
             c->plan = 0;
             return leave(tdm_internal_fail(TDM_ERR_CUDA, "tdm_chan_process: cufftPlanMany failed (M = %d, batch = %lld)", M, n_out));
         }
         c->plan_batch = n_out; c->plan_stride = out_stride;
     }
     const float2* in = reinterpret_cast<const float2*>(wide);
-    const long long n_tiles = (n_out + kTile - 1) / kTile;
-    dim3 grid((unsigned)((M + 255) / 256), (unsigned)(n_tiles < 65535 ? n_tiles : 65535));
+    // instants per CTA: as many as the 192-row window holds (rows = ceil(((mi - 1) D + 31) / M) + T)
+    long long mi = ((long long)(kChanRows - T - 1) * M - (kSlab - 1)) / D;
+    mi = mi > 1024 ? 1024 : (mi < 8 ? 8 : (mi & ~7LL));
+    const long long n_chunks = (n_out + mi - 1) / mi;
+    dim3 grid((unsigned)n_chunks, (unsigned)((M + kSlab - 1) / kSlab));
     cudaEventRecord(c->ev[0], st);
-#define TDM_CHAN_LAUNCH(TT) chan_polyphase_kernel<TT><<<grid, 256, 0, st>>>(in, c->d_hist[c->cur], c->n_hist, c->d_taps, M, D, n_out, c->t_global, c->d_u)
+#define TDM_CHAN_LAUNCH(TT) chan_residue_kernel<TT><<<grid, 256, 0, st>>>(in, n_wide, c->d_hist[c->cur], c->n_hist, c->d_taps, M, D, n_out, (int)mi, c->t_global, c->d_u)
     switch (T) {
         case 8: TDM_CHAN_LAUNCH(8); break;
         case 12: TDM_CHAN_LAUNCH(12); break;
@@ -261,8 +317,13 @@ int tdm_chan_process(tdm_chan* c, const float* wide, int64_t n_wide, float* out,
     }
 #undef TDM_CHAN_LAUNCH
     cudaEventRecord(c->ev[1], st);
-    if (cufft().SetStream(c->plan, st) != 0 || cufft().ExecC2C(c->plan, c->d_u, reinterpret_cast<float2*>(out), CUFFT_INVERSE_) != 0) {
+    if (cufft().SetStream(c->plan, st) != 0 || cufft().ExecC2C(c->plan, c->d_u, c->d_u, CUFFT_INVERSE_) != 0) {
         return leave(tdm_internal_fail(TDM_ERR_CUDA, "tdm_chan_process: cuFFT execution failed"));
+    }
+    {
+        const long long tiles_m = (n_out + 31) / 32;
+        const int tiles_k = (M + 31) / 32;
+        chan_transpose_kernel<<<dim3((unsigned)tiles_m, (unsigned)(tiles_k < 65535 ? tiles_k : 65535)), 256, 0, st>>>(c->d_u, reinterpret_cast<float2*>(out), M, n_out, out_stride);
     }
     cudaEventRecord(c->ev[2], st);
     chan_history_kernel<<<256, 256, 0, st>>>(in, n_wide, c->d_hist[c->cur], c->d_hist[c->cur ^ 1], c->n_hist);

@@ -69,7 +69,7 @@ def measure(args):
         "chain_channel_msps": round(M * n_out / ((ems + dm_ms) * 1e-3) / 1e6, 1),
         "roofline": {"bound": "hbm", "achieved": round(ach, 1), "peak": peak, "unit": "GB/s", "frac": round(ach / peak, 4), "traffic": None,
                      "peak_source": src, "algorithmic_bytes_per_wideband_sample": round(bytes_per_wide, 2),
-                     "kernel": "chan_polyphase_kernel + cuFFT C2C (batched, channel-major output)"},
+                     "kernel": "chan_residue_kernel + cuFFT C2C (batched, in place) + chan_transpose_kernel; the transposing pass is NOT counted in the algorithmic bytes"},
         "parity": "unpinned by the reference (no channeliser there); fp64 defining sum within 2e-5 and wideband -> dibits end to end in tests/test_chan_gpu.py",
     }
 
