@@ -75,7 +75,7 @@ constexpr int kChanRows = 192;               // rows of the staged window: 192 x
 __device__ __forceinline__ long long floor_div(long long a, long long b) { return a >= 0 ? a / b : -((-a + b - 1) / b); }
 template <int T>
 __global__ void __launch_bounds__(256) chan_residue_kernel(const float2* __restrict__ in, long long n_in, const float2* __restrict__ hist, long long n_hist,
-                                                           const float* __restrict__ taps, int M, int D, long long n_out, int mi,
+                                                           const float* __restrict__ taps, int M, int D, long long n_out, int mi, int period,
                                                            long long t0_global /* global index of in[0] */, float2* __restrict__ u) {
     __shared__ float2 xs[kChanRows * kSlab];
     const int lane = threadIdx.x & 31, il = threadIdx.x >> 5;
@@ -100,7 +100,35 @@ __global__ void __launch_bounds__(256) chan_residue_kernel(const float2* __restr
     }
     __syncthreads();
     if (rho >= M) { return; }
-    // this thread's instants: m0 + il, m0 + il + 8, ...  (a, rotation) advance by 8 D per step, reduced without divisions
+    if (period > 0) {
+        // period = M / gcd(D, M) instants later a class meets the SAME branch again (period D is a multiple of M; 36 for
+        // every TETRA raster M = 36 g, D = 25 g): a warp takes the instants k = r (mod period) for a few r in turn, and the
+        // T taps stay in registers for all of them -- shared memory then only carries the samples (128 B per branch sum)
+        const int stepj = (int)(((long long)period * D) / M);
+        for (int r = il; r < period && r < cnt; r += 8) {
+            const unsigned a0 = (unsigned)rem + (unsigned)r * (unsigned)D + (unsigned)(kSlab - 1 - lane);
+            int jr = (int)(a0 / (unsigned)M) + (T - 1);
+            const int pbr = (int)(a0 % (unsigned)M);
+            int pp = pbr - (int)((t0_global + (m0 + r + 1) * D - 1) % M);
+            if (pp < 0) { pp += M; }
+            float h[T];
+#pragma unroll
+            for (int q = 0; q < T; ++q) { h[q] = __ldg(taps + pbr + (long long)q * M); }
+            for (int k = r; k < cnt; k += period) {
+                float2 acc = make_float2(0.f, 0.f);
+#pragma unroll
+                for (int q = 0; q < T; ++q) {
+                    const float2 x = xs[(jr - q) * kSlab + lane];
+                    acc.x = fmaf(h[q], x.x, acc.x);
+                    acc.y = fmaf(h[q], x.y, acc.y);
+                }
+                u[(m0 + k) * M + pp] = acc;
+                jr += stepj;
+            }
+        }
+        return;
+    }
+    // general decimations: this thread's instants are m0 + il, m0 + il + 8, ...  (a, rotation) advance by 8 D per step, reduced without divisions
     const int stepq = (int)((8LL * D) / M), stepr = (int)((8LL * D) % M);
     const unsigned a0 = (unsigned)rem + (unsigned)il * (unsigned)D + (unsigned)(kSlab - 1 - lane);
     int jr = (int)(a0 / (unsigned)M) + (T - 1);                               // row of the newest sample (q = 0)
@@ -306,8 +334,11 @@ int tdm_chan_process(tdm_chan* c, const float* wide, int64_t n_wide, float* out,
     mi = mi > 1024 ? 1024 : (mi < 8 ? 8 : (mi & ~7LL));
     const long long n_chunks = (n_out + mi - 1) / mi;
     dim3 grid((unsigned)n_chunks, (unsigned)((M + kSlab - 1) / kSlab));
+    int gcd_dm = D, tmp = M;
+    while (tmp) { const int t = gcd_dm % tmp; gcd_dm = tmp; tmp = t; }
+    const int period = (M / gcd_dm <= 64 && M / gcd_dm <= mi / 2) ? M / gcd_dm : 0;     // short branch period: taps-in-registers path
     cudaEventRecord(c->ev[0], st);
-#define TDM_CHAN_LAUNCH(TT) chan_residue_kernel<TT><<<grid, 256, 0, st>>>(in, n_wide, c->d_hist[c->cur], c->n_hist, c->d_taps, M, D, n_out, (int)mi, c->t_global, c->d_u)
+#define TDM_CHAN_LAUNCH(TT) chan_residue_kernel<TT><<<grid, 256, 0, st>>>(in, n_wide, c->d_hist[c->cur], c->n_hist, c->d_taps, M, D, n_out, (int)mi, period, c->t_global, c->d_u)
     switch (T) {
         case 8: TDM_CHAN_LAUNCH(8); break;
         case 12: TDM_CHAN_LAUNCH(12); break;

@@ -107,3 +107,38 @@ def test_more_instants_than_a_grid_dimension(pkg, torch_cuda):
         torch.cuda.synchronize()
         assert torch.equal(whole[:, :600_000], a) and torch.equal(whole[:, 600_000:], b)
         assert float(whole[:, -1000:].abs().max()) > 0
+
+
+@pytest.mark.parametrize("M,D,T", [(40, 27, 16), (100, 73, 8), (96, 96, 12), (257, 64, 16)])
+def test_other_rasters_match_the_defining_sum(pkg, torch_cuda, M, D, T):
+    """Rasters other than TETRA's 36 : 25 -- a short branch period that is not 36 (40 : 27 -> 40), long periods that take the
+    general path of the branch-sum kernel (100 : 73, 257 : 64), critical sampling (96 : 96), a slab that is not full
+    (M not a multiple of 32) -- against the float64 defining sum, and chunked == whole."""
+    torch = torch_cuda
+    from oracle import oracle_chan as OC
+    cfg = pkg.chan_default_config(1)
+    cfg.n_channels, cfg.decimation, cfg.taps_per_branch = M, D, T
+    cfg.passband, cfg.stopband = 0.4 * D / M * 2, 0.6 * D / M * 2
+    h = pkg.chan_design(cfg)
+    rng = np.random.default_rng(M + D)
+    n_inst = 700
+    N = D * n_inst
+    x = (rng.standard_normal(N) + 1j * rng.standard_normal(N)).astype(np.complex64)
+    wide = torch.from_numpy(np.stack([x.real, x.imag], axis=1).copy()).cuda()
+    with pkg.Channelizer(cfg) as ch:
+        y = ch.process(wide)
+        ch.reset()
+        parts, pos = [], 0
+        for k in (3, 260, 1, 436):
+            parts.append(ch.process(wide[pos:pos + k * D].contiguous()).cpu().numpy())
+            pos += k * D
+        torch.cuda.synchronize()
+        got = y.cpu().numpy()
+        assert np.array_equal(np.concatenate(parts, axis=1), got), "chunked calls differ from the single call"
+    got = got[..., 0] + 1j * got[..., 1]
+    chans = sorted({0, 1, M // 3, M // 2, M - 1})
+    inst = [0, 1, 2, 35, 36, 37, 255, 256, 257, 500, 699]
+    want = OC.channelize_direct(x.astype(np.complex128), h.astype(np.float64), M, D, chans, inst)
+    rms = np.sqrt(np.mean(np.abs(got) ** 2))
+    err = np.abs(got[np.ix_(chans, inst)] - want).max()
+    assert err < 2e-5 * max(rms, 1.0), (err, rms)
