@@ -49,5 +49,17 @@ with pkg.Demodulator(4, 1024) as dm:
     d2, c2, info2 = dm.process_long_batch(torch.from_numpy(np.stack([long_iq, long_iq])).cuda(), warmup=4096)
     torch.cuda.synchronize()
     assert info["n_segments"] == 4 and info2["n_segments"] == 2, (info, info2)
+# channeliser: the periodic (taps in registers) and the general path of the branch-sum kernel, partial slab, two calls
+for (M, D, T) in ((72, 50, 16), (100, 73, 8)):
+    cfg = pkg.chan_default_config(1)
+    cfg.n_channels, cfg.decimation, cfg.taps_per_branch = M, D, T
+    wide = torch.randn((D * 300, 2), device="cuda")
+    with pkg.Channelizer(cfg) as ch:
+        a = ch.process(wide[:D * 120].contiguous())
+        b = ch.process(wide[D * 120:].contiguous())
+        ch.reset()
+        whole = ch.process(wide)
+        torch.cuda.synchronize()
+        assert torch.equal(torch.cat([a, b], dim=1), whole)
 torch.cuda.synchronize()
 print("sanitize_run ok")
