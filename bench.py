@@ -130,6 +130,12 @@ def cpu_reference_throughput(seconds_hint: float = 15.0):
         counts, _ = a.process_multi(iq, cores)
         dt = time.perf_counter() - t0
         a.close()
+        one = O.OracleA(1, simd=simd)         # the reference's own execution model: one plugin instance, one thread (SURVEY.md 8d i)
+        one.process_multi(iq[:1], 1)
+        t1 = time.perf_counter()
+        one.process_multi(iq[:1], 1)
+        single = n_s / (time.perf_counter() - t1) / 1e6
+        one.close()
         kind = "reference"
         what = ("reference src/dsp/*.cpp (oracle/_ref/libtetra_ref_simd.so: g++ -O3 -mavx2 -mfma, the VOLK stand-in's dot products as 256-bit FMA "
                 "kernels like the ones VOLK dispatches to on this host; same decoded dibits as the generic-order build)" if simd else
@@ -145,6 +151,7 @@ def cpu_reference_throughput(seconds_hint: float = 15.0):
     assert int(counts.min()) > n_s // 2 - 8
     msps = n_ch * n_s / dt / 1e6
     return {"value": round(msps, 3), "unit": "Msamples/s", "cores": cores, "kind": kind,
+            "single_thread_msps": round(single, 3) if kind == "reference" else None,
             "sample": f"{n_ch} channels x {n_s} samples (NOT the GPU arm's 4096 x 4e6: a per-channel rate, channels are "
                       f"independent), one channel per thread, {cores} threads; {what}; {dt:.2f} s wall"}
 
