@@ -90,13 +90,17 @@ __global__ void __launch_bounds__(256) chan_residue_kernel(const float2* __restr
     const long long Jlo = Jb - (T - 1);                                      // first staged row
     const int rows = (int)((rem + (long long)(cnt - 1) * D + (kSlab - 1)) / M) + T;      // <= kChanRows by the host's choice of mi
     if (rho < M) {
+        // asynchronous copies (LDGSTS): every thread has all its rows in flight at once instead of a load -> store chain
+        const uint32_t xs0 = (uint32_t)__cvta_generic_to_shared(xs) + 8u * (uint32_t)lane;
         for (int r = il; r < rows; r += 8) {
             const long long idx = (long long)rho + (Jlo + r) * M;            // local sample index: >= 0 new samples, < 0 carried history
-            float2 v = make_float2(0.f, 0.f);
-            if (idx >= 0) { if (idx < n_in) { v = __ldg(in + idx); } }
-            else if (n_hist + idx >= 0) { v = hist[n_hist + idx]; }
-            xs[r * kSlab + lane] = v;
+            const float2* src = nullptr;
+            if (idx >= 0) { if (idx < n_in) { src = in + idx; } }
+            else if (n_hist + idx >= 0) { src = hist + (n_hist + idx); }
+            if (src) { asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(xs0 + (uint32_t)(r * kSlab * 8)), "l"(src) : "memory"); }
+            else { xs[r * kSlab + lane] = make_float2(0.f, 0.f); }
         }
+        asm volatile("cp.async.commit_group;\n cp.async.wait_group 0;" ::: "memory");
     }
     __syncthreads();
     if (rho >= M) { return; }
