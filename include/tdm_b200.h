@@ -193,13 +193,19 @@ int tdm_process(tdm_handle* h, const float* iq, int64_t in_stride, int32_t count
 /* tdm_process with its arguments in a struct, plus the packed output (TDM_OUT_PACKED):
  *   packed : [C][packed_stride] bytes, packed_stride >= tdm_max_symbols(count) / 4 (tdm_max_symbols is a multiple of 16);
  *            byte j of a row holds symbols 4j .. 4j+3 of this call.
+ *   sample_stride : 0 or 1: the samples of a channel are contiguous (channel-major rows, as above).  s > 1 (TDM_MEM_DEVICE
+ *            only): sample n of channel c is the float pair at iq + 2 * (c * in_stride + n * s) -- with in_stride = 1 and
+ *            s = the number of channels this is INSTANT-major input [sample][channel], what tdm_chan_process_instant_major
+ *            (tdm_chan_b200.h) leaves: the front-end channeliser then needs no transposing pass, and a warp's 32
+ *            channels read one 256-byte row per sample.  (This member was `reserved`, must-be-zero, before: old
+ *            callers are unaffected.)
  * Unused members must be zero. */
 typedef struct tdm_io {
     const float* iq; int64_t in_stride; int32_t count; int32_t mem_kind;
     float* syms; uint8_t* dibits; uint8_t* bits; uint8_t* packed;
     int64_t out_stride, packed_stride;
     int32_t* out_counts;
-    uint32_t out_flags; uint32_t reserved;
+    uint32_t out_flags; uint32_t sample_stride;
 } tdm_io;
 int tdm_process_io(tdm_handle* h, const tdm_io* io);
 

@@ -50,6 +50,12 @@ int tdm_chan_reset(tdm_chan* c);            /* forget the history: the next call
  * asynchronous on cuda_stream (a cudaStream_t).  The first T*M - 1 samples before the first call are zeros. */
 int tdm_chan_process(tdm_chan* c, const float* wide, int64_t n_wide, float* out, int64_t out_stride, void* cuda_stream);
 
+/* The same samples INSTANT-major: out [n_wide / D][row_pitch] float32 pairs, sample m of channel k at
+ * out + 2 * (m * row_pitch + k), row_pitch >= M.  This is the order the batched DFT produces, so the transposing pass of
+ * tdm_chan_process (a third of its time) is not needed; tdm_process_io reads it in place with in_stride = 1,
+ * sample_stride = row_pitch (tdm_b200.h).  Calls of the two kinds can be mixed on one handle. */
+int tdm_chan_process_instant_major(tdm_chan* c, const float* wide, int64_t n_wide, float* out, int64_t row_pitch, void* cuda_stream);
+
 /* kernel time of the last call's two stages in ms (synchronises) */
 int tdm_chan_last_kernel_ms(tdm_chan* c, float* polyphase_ms, float* dft_ms);
 

@@ -130,7 +130,7 @@ class TdmIo(C.Structure):
     _fields_ = [("iq", C.c_void_p), ("in_stride", C.c_int64), ("count", C.c_int32), ("mem_kind", C.c_int32),
                 ("syms", C.c_void_p), ("dibits", C.c_void_p), ("bits", C.c_void_p), ("packed", C.c_void_p),
                 ("out_stride", C.c_int64), ("packed_stride", C.c_int64), ("out_counts", C.c_void_p),
-                ("out_flags", C.c_uint32), ("reserved", C.c_uint32)]
+                ("out_flags", C.c_uint32), ("sample_stride", C.c_uint32)]
 
 
 class TdmError(RuntimeError):

@@ -24,6 +24,7 @@ def _lib():
         L.tdm_chan_destroy.argtypes = [vp]
         L.tdm_chan_reset.argtypes = [vp]
         L.tdm_chan_process.argtypes = [vp, vp, i64, vp, i64, vp]
+        L.tdm_chan_process_instant_major.argtypes = [vp, vp, i64, vp, i64, vp]
         L.tdm_chan_last_kernel_ms.argtypes = [vp, C.POINTER(C.c_float), C.POINTER(C.c_float)]
         L._chan_ready = True
     return L
@@ -70,17 +71,21 @@ class Channelizer:
     def reset(self):
         capi.check(self._lib.tdm_chan_reset(self._h), "tdm_chan_reset")
 
-    def process(self, wide, out=None):
-        """wide: CUDA float32 tensor [N][2], N a multiple of the decimation -> [M][N/D][2] (asynchronous, torch's current stream)."""
+    def process(self, wide, out=None, instant_major: bool = False):
+        """wide: CUDA float32 tensor [N][2], N a multiple of the decimation -> [M][N/D][2], or with instant_major=True
+        [N/D][M][2] (the DFT's own order: no transposing pass; Demodulator.process(..., instant_major=True) reads it in
+        place).  Asynchronous on torch's current stream."""
         import torch
         assert wide.is_cuda and wide.dtype == torch.float32 and wide.dim() == 2 and wide.shape[1] == 2 and wide.is_contiguous()
         n = int(wide.shape[0])
         n_out = n // self.config.decimation
+        M = self.config.n_channels
         if out is None:
-            out = torch.empty((self.config.n_channels, n_out, 2), dtype=torch.float32, device=wide.device)
+            out = torch.empty((n_out, M, 2) if instant_major else (M, n_out, 2), dtype=torch.float32, device=wide.device)
         st = torch.cuda.current_stream(wide.device).cuda_stream
-        capi.check(self._lib.tdm_chan_process(self._h, C.c_void_p(wide.data_ptr()), n, C.c_void_p(out.data_ptr()), out.stride(0) // 2, C.c_void_p(st)),
-                   "tdm_chan_process")
+        fn = self._lib.tdm_chan_process_instant_major if instant_major else self._lib.tdm_chan_process
+        capi.check(fn(self._h, C.c_void_p(wide.data_ptr()), n, C.c_void_p(out.data_ptr()), out.stride(0) // 2, C.c_void_p(st)),
+                   "tdm_chan_process_instant_major" if instant_major else "tdm_chan_process")
         return out
 
     def last_kernel_ms(self):

@@ -108,6 +108,7 @@ void fill_params(const tdm_handle* h, tdm::DemodParams& p) {
     p.n_channels = h->n_channels;
     p.states = h->d_states;
     p.rows_per_channel = 1;
+    p.sample_stride = 1;
     p.channel_stride = 0;
     p.debug_mask = 0;
 }
@@ -251,7 +252,10 @@ int tdm_process_io(tdm_handle* h, const tdm_io* io) {
     if (count < 0) { return fail(TDM_ERR_ARG, "tdm_process: negative count"); }
     if (!out_counts) { return fail(TDM_ERR_ARG, "tdm_process: out_counts is null"); }
     if (count > 0 && !iq) { return fail(TDM_ERR_ARG, "tdm_process: iq is null"); }
-    if (in_stride < count) { return fail(TDM_ERR_ARG, "tdm_process: in_stride < count"); }
+    const long long sstride = io->sample_stride ? (long long)io->sample_stride : 1;
+    if (sstride == 1 && in_stride < count) { return fail(TDM_ERR_ARG, "tdm_process: in_stride < count"); }
+    if (sstride != 1 && mem_kind != TDM_MEM_DEVICE) { return fail(TDM_ERR_ARG, "tdm_process: sample_stride needs TDM_MEM_DEVICE (host buffers are staged row by row)"); }
+    if (sstride != 1 && in_stride < 1) { return fail(TDM_ERR_ARG, "tdm_process: in_stride < 1"); }
     if (out_flags & ~(TDM_OUT_SYMBOLS | TDM_OUT_DIBITS | TDM_OUT_BITS | TDM_OUT_PACKED)) { return fail(TDM_ERR_ARG, "tdm_process: unknown bits in out_flags"); }
     if (((out_flags & TDM_OUT_SYMBOLS) && !syms) || ((out_flags & TDM_OUT_DIBITS) && !dibits) || ((out_flags & TDM_OUT_BITS) && !bits) ||
         ((out_flags & TDM_OUT_PACKED) && !packed)) {
@@ -274,6 +278,7 @@ int tdm_process_io(tdm_handle* h, const tdm_io* io) {
     if (mem_kind == TDM_MEM_DEVICE) {
         p.iq = reinterpret_cast<const float2*>(iq);
         p.in_stride = in_stride;
+        p.sample_stride = sstride;
         p.syms = (out_flags & TDM_OUT_SYMBOLS) ? reinterpret_cast<float2*>(syms) : nullptr;
         p.dibits = (out_flags & TDM_OUT_DIBITS) ? dibits : nullptr;
         p.bits = (out_flags & TDM_OUT_BITS) ? bits : nullptr;

@@ -202,7 +202,7 @@ struct tdm_chan {
     float2* d_u = nullptr;
     long long u_cap = 0;             // instants the branch-sum buffer holds
     cufftHandle plan = 0;
-    long long plan_batch = 0, plan_stride = 0;
+    long long plan_batch = 0, plan_stride = 0;      // plan_stride: distance between consecutive instants of the DFT's output (M: in place)
     cudaEvent_t ev[3] = { nullptr, nullptr, nullptr };
 };
 
@@ -303,13 +303,21 @@ int tdm_chan_reset(tdm_chan* c) {
     return ok ? TDM_OK : tdm_internal_fail(TDM_ERR_CUDA, "tdm_chan_reset: memset failed");
 }
 
+static int chan_process(tdm_chan* c, const float* wide, int64_t n_wide, float* out, int64_t out_stride, bool instant_major, void* cuda_stream);
 int tdm_chan_process(tdm_chan* c, const float* wide, int64_t n_wide, float* out, int64_t out_stride, void* cuda_stream) {
+    return chan_process(c, wide, n_wide, out, out_stride, false, cuda_stream);
+}
+int tdm_chan_process_instant_major(tdm_chan* c, const float* wide, int64_t n_wide, float* out, int64_t row_pitch, void* cuda_stream) {
+    return chan_process(c, wide, n_wide, out, row_pitch, true, cuda_stream);
+}
+static int chan_process(tdm_chan* c, const float* wide, int64_t n_wide, float* out, int64_t out_stride, bool instant_major, void* cuda_stream) {
     if (!c || n_wide < 0 || (n_wide > 0 && (!wide || !out))) { return tdm_internal_fail(TDM_ERR_ARG, "tdm_chan_process: bad arguments"); }
     const int M = c->cfg.n_channels, D = c->cfg.decimation, T = c->cfg.taps_per_branch;
     if (n_wide % D) { return tdm_internal_fail(TDM_ERR_ARG, "tdm_chan_process: n_wide must be a multiple of the decimation %d", D); }
     const long long n_out = n_wide / D;
     if (n_out == 0) { return TDM_OK; }
-    if (out_stride < n_out) { return tdm_internal_fail(TDM_ERR_ARG, "tdm_chan_process: out_stride < n_wide / D"); }
+    if (!instant_major && out_stride < n_out) { return tdm_internal_fail(TDM_ERR_ARG, "tdm_chan_process: out_stride < n_wide / D"); }
+    if (instant_major && (out_stride < M || out_stride > 0x7fffffffLL)) { return tdm_internal_fail(TDM_ERR_ARG, "tdm_chan_process_instant_major: row_pitch < M"); }
     if (n_out > 0x7fffffffLL) { return tdm_internal_fail(TDM_ERR_ARG, "tdm_chan_process: too many output instants for one call"); }
     cudaStream_t st = (cudaStream_t)cuda_stream;
     int prev = -1;
@@ -321,16 +329,17 @@ int tdm_chan_process(tdm_chan* c, const float* wide, int64_t n_wide, float* out,
         if (cudaMalloc(&c->d_u, sizeof(float2) * (size_t)n_out * (size_t)M) != cudaSuccess) { return leave(tdm_internal_fail(TDM_ERR_NOMEM, "tdm_chan_process: cannot allocate the branch-sum buffer")); }
         c->u_cap = n_out;
     }
-    if (!c->plan || c->plan_batch != n_out || c->plan_stride != out_stride) {
+    const long long dft_dist = instant_major ? out_stride : M;
+    if (!c->plan || c->plan_batch != n_out || c->plan_stride != dft_dist) {
         if (c->plan) { cufft().Destroy(c->plan); c->plan = 0; }
         int n[1] = { M }, inembed[1] = { M }, onembed[1] = { M };
         // instant m at u + m M, unit stride, in place; chan_transpose_kernel then writes channel k of instant m at out + k * out_stride + m
         // (cuFFT can write that layout itself -- ostride = out_stride, odist = 1 -- but took 0.89 ms for 16384 x 4608 that way)
-        if (cufft().PlanMany(&c->plan, 1, n, inembed, 1, M, onembed, 1, M, CUFFT_C2C_, (int)n_out) != 0) {
+        if (cufft().PlanMany(&c->plan, 1, n, inembed, 1, M, onembed, 1, (int)dft_dist, CUFFT_C2C_, (int)n_out) != 0) {
             c->plan = 0;
             return leave(tdm_internal_fail(TDM_ERR_CUDA, "tdm_chan_process: cufftPlanMany failed (M = %d, batch = %lld)", M, n_out));
         }
-        c->plan_batch = n_out; c->plan_stride = out_stride;
+        c->plan_batch = n_out; c->plan_stride = dft_dist;
     }
     const float2* in = reinterpret_cast<const float2*>(wide);
     // instants per CTA: as many as the 192-row window holds (rows = ceil(((mi - 1) D + 31) / M) + T)
@@ -352,10 +361,10 @@ int tdm_chan_process(tdm_chan* c, const float* wide, int64_t n_wide, float* out,
     }
 #undef TDM_CHAN_LAUNCH
     cudaEventRecord(c->ev[1], st);
-    if (cufft().SetStream(c->plan, st) != 0 || cufft().ExecC2C(c->plan, c->d_u, c->d_u, CUFFT_INVERSE_) != 0) {
+    if (cufft().SetStream(c->plan, st) != 0 || cufft().ExecC2C(c->plan, c->d_u, instant_major ? reinterpret_cast<float2*>(out) : c->d_u, CUFFT_INVERSE_) != 0) {
         return leave(tdm_internal_fail(TDM_ERR_CUDA, "tdm_chan_process: cuFFT execution failed"));
     }
-    {
+    if (!instant_major) {
         const long long tiles_m = (n_out + 31) / 32;
         const int tiles_k = (M + 31) / 32;
         chan_transpose_kernel<<<dim3((unsigned)tiles_m, (unsigned)(tiles_k < 65535 ? tiles_k : 65535)), 256, 0, st>>>(c->d_u, reinterpret_cast<float2*>(out), M, n_out, out_stride);

@@ -99,12 +99,13 @@ __global__ void __launch_bounds__(128) demod_tpc_kernel(const __grid_constant__ 
     __syncthreads();   // bank visible
 
     const float2* __restrict__ in = row_input(p, ch);
+    const long long ss = p.sample_stride;
     const int count = p.count;
     const int nblk = (count + T - 1) / T;
 
     float2 cur[T], nxt[T];
 #pragma unroll
-    for (int i = 0; i < T; ++i) { cur[i] = (i < count) ? __ldg(in + i) : make_float2(0.f, 0.f); }
+    for (int i = 0; i < T; ++i) { cur[i] = (i < count) ? __ldg(in + i * ss) : make_float2(0.f, 0.f); }
     const SymConsts kc = load_sym_consts(p);
     const LoopConsts lc = load_loop_consts(p);
 
@@ -117,7 +118,7 @@ __global__ void __launch_bounds__(128) demod_tpc_kernel(const __grid_constant__ 
 #pragma unroll
         for (int i = 0; i < T; ++i) {
             const int n = n0 + T + i;
-            nxt[i] = (n < count) ? __ldg(in + n) : make_float2(0.f, 0.f);
+            nxt[i] = (n < count) ? __ldg(in + n * ss) : make_float2(0.f, 0.f);
         }
 
         // ---- old part: history terms of all T outputs (independent of this block's feedback).

@@ -28,6 +28,8 @@ struct DemodParams {
     const float* bank;              // device [128][8] interpolator polyphase bank
     const float2* iq;               // [C][in_stride]
     long long in_stride;
+    long long sample_stride;        // samples of a row are this many float2 apart (1: channel-major rows; M with in_stride 1:
+                                    // instant-major [sample][channel], what the channeliser leaves without its transposing pass)
     long long channel_stride;       // only with rows_per_channel > 1 (see row_input() in tdm_kernels.cu)
     int rows_per_channel;           // 0 / 1: every row is a channel
     int count;                      // samples per channel this launch

@@ -238,7 +238,7 @@ __device__ __forceinline__ void fir_tick(const WsSmem& sm, const float* __restri
 #define TDM_ROLE_ON(r) true
 #endif
 
-template <int PLACEMENT, int CTAS, bool RE_ONLY>
+template <int PLACEMENT, int CTAS, bool RE_ONLY, bool STRIDED = false>
 __global__ void __launch_bounds__(Placement<PLACEMENT>::warps * 32, CTAS) demod_ws4_kernel(const __grid_constant__ DemodParams p) {
     constexpr int T = kT;
     constexpr int NT = Placement<PLACEMENT>::warps * 32;
@@ -295,21 +295,41 @@ __global__ void __launch_bounds__(Placement<PLACEMENT>::warps * 32, CTAS) demod_
         float g = sp->agc_gain;
         const float2* __restrict__ in = row_input(p, ch);
         const LoopConsts lc = load_loop_consts(p);
+        // STRIDED (a kernel instantiation of its own: the ordinary one keeps its code byte for byte -- a generic body cost
+        // it 11 %): the samples of a row are sample_stride apart (instant-major input: the 32 lanes of a sample sit side
+        // by side, one 256-byte row per load)
+        const long long ss = STRIDED ? p.sample_stride : 1;
+        const unsigned sso = (unsigned)ss;                    // sample_stride comes from a 32-bit field
+        // instant-major input and a full warp of channels: the warp's 32 samples of an instant are one 256-byte row
+        const bool warp_rows_contiguous = STRIDED && p.in_stride == 1 && p.rows_per_channel <= 1 && blockIdx.x * 32 + 32 <= p.n_channels;
+        const float2* __restrict__ warp_base = p.iq + (long long)blockIdx.x * 32;
         float2 cur[T], nxt[T];
 #pragma unroll
-        for (int i = 0; i < T; ++i) { cur[i] = (i < count) ? __ldg(in + i) : make_float2(0.f, 0.f); }
+        for (int i = 0; i < T; ++i) { cur[i] = (i < count) ? __ldg(in + i * ss) : make_float2(0.f, 0.f); }
 #pragma unroll 1
         for (int t = -1; t <= t_last; ++t) {
             const int b = t + 1;
             if (b < nblk && TDM_ROLE_ON(kRAgc)) {
                 const int n0 = b * T;
                 const int valid = min(T, count - n0);
+                if (!STRIDED) {
 #pragma unroll
-                for (int i = 0; i < T; ++i) {
-                    const int n = n0 + T + i;
-                    nxt[i] = (n < count) ? __ldg(in + n) : make_float2(0.f, 0.f);
+                    for (int i = 0; i < T; ++i) {
+                        const int n = n0 + T + i;
+                        nxt[i] = (n < count) ? __ldg(in + n) : make_float2(0.f, 0.f);
+                    }
+                } else {
+                    // one 64-bit pointer per tick, the eight rows at uniform 32-bit offsets from it
+                    const float2* __restrict__ nx = in + (long long)(n0 + T) * ss;
+#pragma unroll
+                    for (int i = 0; i < T; ++i) { nxt[i] = (n0 + T + i < count) ? __ldg(nx + (unsigned)i * sso) : make_float2(0.f, 0.f); }
                 }
-                if (n0 + 5 * T < count) { asm volatile("prefetch.global.L2 [%0];" :: "l"(in + n0 + 5 * T)); }
+                if (!STRIDED) {
+                    if (n0 + 5 * T < count) { asm volatile("prefetch.global.L2 [%0];" :: "l"(in + n0 + 5 * T)); }
+                } else if (warp_rows_contiguous && n0 + 6 * T <= count) {
+                    // one instruction per tick: lane l asks for the 128-byte line (l >> 3) & 1 of row 5 T + (l & 7) of its warp's channels
+                    asm volatile("prefetch.global.L2 [%0];" :: "l"(warp_base + 16 * ((lane >> 3) & 1) + (long long)(n0 + 5 * T + (lane & 7)) * ss));
+                }
                 float2 y[T];
 #pragma unroll
                 for (int i = 0; i < T; ++i) {
@@ -611,6 +631,14 @@ int launch_ws4(const DemodParams& p_in, cudaStream_t stream, int placement, int 
         if (p.fastamp_re_only) { go(demod_ws4_kernel<PL, CT, true>, Placement<PL>::warps); }                        \
         else { go(demod_ws4_kernel<PL, CT, false>, Placement<PL>::warps); }                                         \
         return cudaGetLastError() == cudaSuccess ? 1 : -1;                                                           \
+    }
+    if (p.sample_stride != 1) {       // strided input: placement 0 only
+        if (ctas_per_sm == 1) {
+            if (p.fastamp_re_only) { go(demod_ws4_kernel<0, 1, true, true>, Placement<0>::warps); } else { go(demod_ws4_kernel<0, 1, false, true>, Placement<0>::warps); }
+        } else {
+            if (p.fastamp_re_only) { go(demod_ws4_kernel<0, 2, true, true>, Placement<0>::warps); } else { go(demod_ws4_kernel<0, 2, false, true>, Placement<0>::warps); }
+        }
+        return cudaGetLastError() == cudaSuccess ? 1 : -1;
     }
     TDM_WS4_CASE(0, 1) TDM_WS4_CASE(1, 1) TDM_WS4_CASE(2, 1) TDM_WS4_CASE(3, 1)
     TDM_WS4_CASE(0, 2) TDM_WS4_CASE(1, 2) TDM_WS4_CASE(2, 2) TDM_WS4_CASE(3, 2)

@@ -136,14 +136,17 @@ class Demodulator:
 
     # -- the hot call
     def process(self, iq, symbols: bool = False, dibits: bool = True, bits: bool = False, packed: bool = False,
-                out: DemodResult | None = None) -> DemodResult:
+                out: DemodResult | None = None, instant_major: bool = False) -> DemodResult:
         """iq: [C][N][2] float32 -- a CUDA torch tensor (zero-copy, asynchronous on the handle's stream)
-        or a numpy array (staged through the library, synchronous)."""
+        or a numpy array (staged through the library, synchronous).  instant_major=True (CUDA tensors only): iq is
+        [N][C][2], the order the channeliser's DFT leaves (tdm_io.sample_stride)."""
         flags = (capi.TDM_OUT_SYMBOLS if symbols else 0) | (capi.TDM_OUT_DIBITS if dibits else 0) | \
                 (capi.TDM_OUT_BITS if bits else 0) | (capi.TDM_OUT_PACKED if packed else 0)
         if isinstance(iq, np.ndarray):
+            if instant_major:
+                raise ValueError("instant-major input needs a CUDA tensor")
             return self._process_host(iq, flags)
-        return self._process_device(iq, flags, out)
+        return self._process_device(iq, flags, out, instant_major)
 
     def _process_host(self, iq: np.ndarray, flags: int) -> DemodResult:
         iq = np.ascontiguousarray(iq, dtype=np.float32)
@@ -161,13 +164,18 @@ class Demodulator:
         capi.check(self._lib.tdm_process_io(self._h, C.byref(io)), "tdm_process_io")
         return DemodResult(counts, syms, dib, bit, pk)
 
-    def _process_device(self, iq, flags: int, out: DemodResult | None) -> DemodResult:
+    def _process_device(self, iq, flags: int, out: DemodResult | None, instant_major: bool = False) -> DemodResult:
         torch = _torch()
-        if not (iq.is_cuda and iq.dtype == torch.float32 and iq.dim() == 3 and iq.shape[2] == 2 and
-                iq.shape[0] == self.n_channels and iq.stride(2) == 1 and iq.stride(1) == 2):
-            raise ValueError("iq must be a CUDA float32 tensor [C][N][2] with contiguous rows")
-        n = iq.shape[1]
-        in_stride = iq.stride(0) // 2
+        if instant_major:
+            if not (iq.is_cuda and iq.dtype == torch.float32 and iq.dim() == 3 and iq.shape[2] == 2 and
+                    iq.shape[1] == self.n_channels and iq.stride(2) == 1 and iq.stride(1) == 2 and iq.stride(0) % 2 == 0):
+                raise ValueError("iq must be a CUDA float32 tensor [N][C][2] with contiguous instants")
+            n, in_stride, sample_stride = iq.shape[0], 1, iq.stride(0) // 2
+        else:
+            if not (iq.is_cuda and iq.dtype == torch.float32 and iq.dim() == 3 and iq.shape[2] == 2 and
+                    iq.shape[0] == self.n_channels and iq.stride(2) == 1 and iq.stride(1) == 2):
+                raise ValueError("iq must be a CUDA float32 tensor [C][N][2] with contiguous rows")
+            n, in_stride, sample_stride = iq.shape[1], iq.stride(0) // 2, 0
         s = self.max_symbols(n)
         dev = iq.device
         # device tensors belong to torch's stream-ordered allocator: enqueue on torch's current stream so
@@ -189,7 +197,7 @@ class Demodulator:
             stride = s
         p = lambda t: None if t is None else t.data_ptr()
         io = capi.TdmIo(p(iq), in_stride, n, capi.TDM_MEM_DEVICE, p(out.symbols), p(out.dibits), p(out.bits), p(out.packed),
-                        stride, 0 if out.packed is None else out.packed.shape[1], p(out.counts), flags, 0)
+                        stride, 0 if out.packed is None else out.packed.shape[1], p(out.counts), flags, sample_stride)
         capi.check(self._lib.tdm_process_io(self._h, C.byref(io)), "tdm_process_io")
         return out
 

@@ -142,3 +142,28 @@ def test_other_rasters_match_the_defining_sum(pkg, torch_cuda, M, D, T):
     rms = np.sqrt(np.mean(np.abs(got) ** 2))
     err = np.abs(got[np.ix_(chans, inst)] - want).max()
     assert err < 2e-5 * max(rms, 1.0), (err, rms)
+
+
+def test_instant_major_output_and_chain(O, pkg, torch_cuda):
+    """tdm_chan_process_instant_major leaves [instant][channel] -- the batched DFT's own order, no transposing pass -- and the
+    demodulator reads it in place (tdm_io.sample_stride): the same samples as the channel-major call, and the same
+    dibits out of the chain."""
+    torch = torch_cuda
+    cfg = pkg.chan_default_config(2)             # 72 channels
+    M, D = cfg.n_channels, cfg.decimation
+    g = torch.Generator(device="cuda").manual_seed(11)
+    wide = torch.randn((D * 3000, 2), generator=g, device="cuda", dtype=torch.float32)
+    with pkg.Channelizer(cfg) as ch:
+        a = ch.process(wide)
+        ch.reset()
+        b1 = ch.process(wide[:D * 1000].contiguous(), instant_major=True)
+        b2 = ch.process(wide[D * 1000:].contiguous(), instant_major=True)
+        torch.cuda.synchronize()
+        b = torch.cat([b1, b2], dim=0)
+        assert b.shape == (3000, M, 2)
+        assert torch.equal(b.permute(1, 0, 2), a)
+    with pkg.Demodulator(M, 3000) as d1, pkg.Demodulator(M, 3000) as d2:
+        r1 = d1.process(a, dibits=True)
+        r2 = d2.process(b, dibits=True, instant_major=True)
+        torch.cuda.synchronize()
+        assert torch.equal(r1.counts, r2.counts) and torch.equal(r1.dibits, r2.dibits)

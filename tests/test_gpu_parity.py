@@ -571,3 +571,24 @@ def test_more_rows_than_a_grid_dimension(O, pkg, torch_cuda):
         assert bool(((ud[:, :S].view(R, C0, S) == d) | ~valid).all())
     with pytest.raises(Exception):
         pkg.BurstSync(70000, 1024)                  # one grid row per channel there: refused, not mis-launched
+
+
+@pytest.mark.parametrize("variant", [1, 2, 4, 8])
+@pytest.mark.parametrize("n_channels,n_samples,pitch_extra", [(64, 9001, 0), (37, 12000, 3), (5, 4097, 0)])
+def test_instant_major_input_is_the_same_stream(O, pkg, torch_cuda, variant, n_channels, n_samples, pitch_extra):
+    """tdm_io.sample_stride: the same capture handed over as [sample][channel] (what the channeliser's DFT leaves) instead
+    of [channel][sample] -- every kernel mapping, full and partial warps, a row pitch wider than the channel count --
+    gives the checker's bits and loop state, bit for bit."""
+    torch = torch_cuda
+    iq = O.generate(n_channels, n_samples)
+    ob = O.OracleB(n_channels)
+    cb, sb, db, _ = ob.process(iq)
+    buf = torch.zeros((n_samples, n_channels + pitch_extra, 2), dtype=torch.float32, device="cuda")
+    buf[:, :n_channels] = torch.from_numpy(iq).cuda().permute(1, 0, 2)
+    with pkg.Demodulator(n_channels, n_samples) as dm:
+        dm.set_kernel_variant(variant)
+        res = dm.process(buf[:, :n_channels], symbols=True, dibits=True, instant_major=True)
+        assert_matches_oracle_b(O, dm, ob, res, cb, sb, db)
+    with pkg.Demodulator(n_channels, n_samples) as dm, pytest.raises(Exception):
+        io_host = np.zeros((n_samples, n_channels, 2), np.float32)
+        dm.process(io_host, instant_major=True)

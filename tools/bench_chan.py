@@ -28,29 +28,36 @@ def measure(args):
     n_wide = n_out * D
     gen = torch.Generator(device=dev).manual_seed(1)
     wide = torch.randn((n_wide, 2), generator=gen, device=dev, dtype=torch.float32)
-    out = torch.empty((M, n_out, 2), dtype=torch.float32, device=dev)
+    out = torch.empty((M, n_out, 2), dtype=torch.float32, device=dev)         # channel-major (tdm_chan_process, with the transposing pass)
+    out_im = torch.empty((n_out, M, 2), dtype=torch.float32, device=dev)      # instant-major (tdm_chan_process_instant_major)
     with pkg.Channelizer(cfg) as ch, pkg.Demodulator(M, 1024) as dm:
         dm.use_torch_stream()
         S = dm.max_symbols(n_out)
         res = pkg.DemodResult(torch.empty(M, dtype=torch.int32, device=dev), None, torch.empty((M, S), dtype=torch.uint8, device=dev), None)
         for _ in range(args.warmup):
             ch.process(wide, out=out)
-            dm.process(out, dibits=True, out=res)
+            ch.process(wide, out=out_im, instant_major=True)
+            dm.process(out_im, dibits=True, out=res, instant_major=True)
         torch.cuda.synchronize()
-        e = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
-        pm = dm_ms = 0.0
-        ems = 0.0
+        e = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+        pm = dm_ms = ems = cm_ms = 0.0
         for _ in range(args.steps):
             e[0].record()
-            ch.process(wide, out=out)
+            ch.process(wide, out=out_im, instant_major=True)
             e[1].record()
-            dm.process(out, dibits=True, out=res)
+            dm.process(out_im, dibits=True, out=res, instant_major=True)
             e[2].record()
+            ch.process(wide, out=out)
+            e[3].record()
             torch.cuda.synchronize()
             ems += e[0].elapsed_time(e[1])
             dm_ms += e[1].elapsed_time(e[2])
+            cm_ms += e[2].elapsed_time(e[3])
+            ch.process(wide, out=out_im, instant_major=True)
+            torch.cuda.synchronize()
             a, b = ch.last_kernel_ms()
             pm += a
+        cm_ms /= args.steps
         ems /= args.steps; dm_ms /= args.steps; pm /= args.steps
         # ---- end to end from HOST memory: one pinned wideband buffer in, dibits + counts out, in `parts` sub-chunks so the copy of
         # chunk k+1 crosses PCIe while chunk k is channelised and demodulated (two device buffers, copy stream + compute stream)
@@ -63,7 +70,7 @@ def measure(args):
         dib_h = torch.empty((parts, M, Sc), dtype=torch.uint8).pin_memory()
         cnt_h = torch.empty((parts, M), dtype=torch.int32).pin_memory()
         wbuf = [torch.empty((ci * D, 2), dtype=torch.float32, device=dev) for _ in range(2)]
-        obuf = torch.empty((M, ci, 2), dtype=torch.float32, device=dev)
+        obuf = torch.empty((ci, M, 2), dtype=torch.float32, device=dev)
         rbuf = [pkg.DemodResult(torch.empty(M, dtype=torch.int32, device=dev), None, torch.empty((M, Sc), dtype=torch.uint8, device=dev), None) for _ in range(2)]
         copy_s, back_s, comp_s = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev), torch.cuda.current_stream(dev)
         landed = [torch.cuda.Event() for _ in range(2)]
@@ -79,11 +86,11 @@ def measure(args):
                     wbuf[b].copy_(wide_h[k * ci * D:(k + 1) * ci * D], non_blocking=True)
                     landed[b].record(copy_s)
                 comp_s.wait_event(landed[b])
-                ch.process(wbuf[b], out=obuf)
+                ch.process(wbuf[b], out=obuf, instant_major=True)
                 freed[b].record(comp_s)
                 if k >= 2:
                     comp_s.wait_event(drained[b])
-                dm.process(obuf, dibits=True, out=rbuf[b])
+                dm.process(obuf, dibits=True, out=rbuf[b], instant_major=True)
                 ready = torch.cuda.Event()
                 ready.record(comp_s)
                 with torch.cuda.stream(back_s):               # results go back on a stream of their own: the next H2D must not queue behind them
@@ -111,7 +118,8 @@ def measure(args):
     return {
         "metric": "wideband complex Msamples/s through the channeliser", "value": round(n_wide / (ems * 1e-3) / 1e6, 1), "unit": "Msamples/s",
         "channel_msps": round(M * n_out / (ems * 1e-3) / 1e6, 1), "ms_per_step": round(ems, 3), "polyphase_kernel_ms": round(pm, 3),
-        "dft_ms": round(ems - pm, 3), "n_gpus": 1, "steps": args.steps, "warmup": args.warmup, "dtype": "f32", "data": "synthetic (white noise)",
+        "dft_ms": round(ems - pm, 3), "layout": "instant-major [sample][channel] (tdm_chan_process_instant_major; read in place by tdm_process_io with sample_stride)",
+        "channel_major_ms_per_step": round(cm_ms, 3), "n_gpus": 1, "steps": args.steps, "warmup": args.warmup, "dtype": "f32", "data": "synthetic (white noise)",
         "config": {"workload": f"{M} channels on a 25 kHz raster from one {0.9 * args.g:.1f} MS/s capture (D = {D}, {cfg.taps_per_branch} taps per branch), "
                                f"{n_out} output samples per channel per step"},
         "then_demodulated_ms": round(dm_ms, 3),
@@ -123,7 +131,7 @@ def measure(args):
         "chain_channel_msps": round(M * n_out / ((ems + dm_ms) * 1e-3) / 1e6, 1),
         "roofline": {"bound": "hbm", "achieved": round(ach, 1), "peak": peak, "unit": "GB/s", "frac": round(ach / peak, 4), "traffic": None,
                      "peak_source": src, "algorithmic_bytes_per_wideband_sample": round(bytes_per_wide, 2),
-                     "kernel": "chan_residue_kernel + cuFFT C2C (batched, in place) + chan_transpose_kernel; the transposing pass is NOT counted in the algorithmic bytes"},
+                     "kernel": "chan_residue_kernel + cuFFT C2C (batched)"},
         "parity": "unpinned by the reference (no channeliser there); fp64 defining sum within 2e-5 and wideband -> dibits end to end in tests/test_chan_gpu.py",
     }
 
