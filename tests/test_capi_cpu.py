@@ -191,7 +191,10 @@ def test_multi_gpu_example_runs(pkg, tmp_path):
         pytest.skip("no CUDA device")
     exe = _build_sharded_gather(pkg, tmp_path)
     world = min(2, torch.cuda.device_count())
-    procs = [subprocess.Popen([str(exe), str(r), str(world), str(tmp_path / "id"), "64", "60000"], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+    # single node: keep NCCL's bootstrap on the loopback interface and off InfiniBand probing (on some boxes the system
+    # libnccl spent two minutes there; the container's hostname may not resolve)
+    env = dict(os.environ, NCCL_SOCKET_IFNAME="lo", NCCL_IB_DISABLE="1")
+    procs = [subprocess.Popen([str(exe), str(r), str(world), str(tmp_path / "id"), "64", "60000"], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, env=env)
              for r in range(world)]
     outs = [p.communicate(timeout=300) for p in procs]
     for p, (o, e) in zip(procs, outs):
