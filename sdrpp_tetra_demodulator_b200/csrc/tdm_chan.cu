@@ -2,16 +2,17 @@
 //
 //   y_c[m] = sum_n h[n] x[t_m - n] e^{-j 2 pi c (t_m - n)/M},  t_m = (m+1) D - 1
 //          = sum_p e^{+j 2 pi c (p - r_m)/M} v_m[p],   v_m[p] = sum_{q<T} h[p + q M] x[t_m - p - q M],   r_m = t_m mod M
-// so one output instant = M branch sums (kernel below), rotated by r_m, then an M-point inverse DFT (cuFFT, batched
-// over instants, writing channel-major so the demodulator can read its rows in place).
+// so one output instant = M branch sums (chan_residue_kernel), rotated by r_m, then an M-point inverse DFT (cuFFT, batched
+// over instants).  The DFT leaves [instant][channel]: tdm_chan_process_instant_major hands that over as it is (the
+// demodulator reads it in place, tdm_io.sample_stride), tdm_chan_process transposes it into channel-major rows.
 //
-// This stage is HBM-bound: per wideband sample 8 B are read once (the T * M / D re-reads of a sample by different
-// branch sums hit L2: the window an output tile needs is T M + tile D samples), the branch sums are written and read
-// once (8 B * M / D each) and the channel samples written once (8 B * M / D): 8 + 3 * 8 * 36/25 = 42.6 B per wideband
-// sample.  Arithmetic: 2 T FMAs per branch sum (T = 16: 32) + 5 log2 M flops per channel sample -- against 390 FMAs
-// per channel sample in the demodulator behind it.  Tensor cores: the DFT could be run as a [M x M] GEMM, but that is
-// 8 M / (5 log2 M) = 30 .. 600 times the FFT's flops and would have to be split-TF32 to keep fp32's dynamic range next
-// to a strong neighbour; an HBM-bound fp32 FFT is the right tool.
+// This stage is HBM-bound: per wideband sample 8 B are read once (every sample belongs to one residue slab, which stages
+// it in shared memory once), the branch sums are written and read once (8 B * M / D each) and the channel samples
+// written once (8 B * M / D): 8 + 3 * 8 * 36/25 = 42.6 B per wideband sample (the channel-major variant moves another
+// 2 * 8 * M / D in its transposing pass).  Arithmetic: 2 T FMAs per branch sum (T = 16: 32) + 5 log2 M flops per channel
+// sample -- against 390 FMAs per channel sample in the demodulator behind it.  Tensor cores: the DFT could be run as a
+// [M x M] GEMM, but that is 8 M / (5 log2 M) = 30 .. 600 times the FFT's flops and would have to be split-TF32 to keep
+// fp32's dynamic range next to a strong neighbour; an HBM-bound fp32 FFT is the right tool.
 #include <cuda_runtime.h>
 #include <dlfcn.h>
 #include <cmath>
