@@ -56,6 +56,17 @@ int tdm_chan_process(tdm_chan* c, const float* wide, int64_t n_wide, float* out,
  * sample_stride = row_pitch (tdm_b200.h).  Calls of the two kinds can be mixed on one handle. */
 int tdm_chan_process_instant_major(tdm_chan* c, const float* wide, int64_t n_wide, float* out, int64_t row_pitch, void* cuda_stream);
 
+/* Both of the above with the input format as an argument.  TDM_CHAN_IN_CS16: `wide` is n_wide interleaved int16 pairs
+ * (re, im) -- what SDR hardware and baseband recordings deliver -- taken as s / 32768 (the scale of the reference's own
+ * volk_16i_s32f_convert_32f call, src/dsp/osmotetra_dec.h:219): half the bytes across PCIe and from HBM; results are
+ * bit-identical to feeding the converted floats.  Formats can be mixed from call to call (the history is kept as floats).
+ * pitch: out_stride (channel-major) or row_pitch (instant-major). */
+#define TDM_CHAN_IN_CF32 0
+#define TDM_CHAN_IN_CS16 1
+#define TDM_CHAN_OUT_CHANNEL_MAJOR 0
+#define TDM_CHAN_OUT_INSTANT_MAJOR 1
+int tdm_chan_process_ex(tdm_chan* c, const void* wide, int32_t in_format, int64_t n_wide, float* out, int64_t pitch, int32_t out_layout, void* cuda_stream);
+
 /* kernel time of the last call's two stages in ms (synchronises) */
 int tdm_chan_last_kernel_ms(tdm_chan* c, float* polyphase_ms, float* dft_ms);
 

@@ -25,6 +25,7 @@ def _lib():
         L.tdm_chan_reset.argtypes = [vp]
         L.tdm_chan_process.argtypes = [vp, vp, i64, vp, i64, vp]
         L.tdm_chan_process_instant_major.argtypes = [vp, vp, i64, vp, i64, vp]
+        L.tdm_chan_process_ex.argtypes = [vp, vp, i32, i64, vp, i64, i32, vp]
         L.tdm_chan_last_kernel_ms.argtypes = [vp, C.POINTER(C.c_float), C.POINTER(C.c_float)]
         L._chan_ready = True
     return L
@@ -72,20 +73,21 @@ class Channelizer:
         capi.check(self._lib.tdm_chan_reset(self._h), "tdm_chan_reset")
 
     def process(self, wide, out=None, instant_major: bool = False):
-        """wide: CUDA float32 tensor [N][2], N a multiple of the decimation -> [M][N/D][2], or with instant_major=True
+        """wide: CUDA float32 (or int16: CS16, value s / 32768) tensor [N][2], N a multiple of the decimation -> [M][N/D][2], or with instant_major=True
         [N/D][M][2] (the DFT's own order: no transposing pass; Demodulator.process(..., instant_major=True) reads it in
         place).  Asynchronous on torch's current stream."""
         import torch
-        assert wide.is_cuda and wide.dtype == torch.float32 and wide.dim() == 2 and wide.shape[1] == 2 and wide.is_contiguous()
+        assert wide.is_cuda and wide.dtype in (torch.float32, torch.int16) and wide.dim() == 2 and wide.shape[1] == 2 and wide.is_contiguous()
         n = int(wide.shape[0])
         n_out = n // self.config.decimation
         M = self.config.n_channels
         if out is None:
             out = torch.empty((n_out, M, 2) if instant_major else (M, n_out, 2), dtype=torch.float32, device=wide.device)
         st = torch.cuda.current_stream(wide.device).cuda_stream
-        fn = self._lib.tdm_chan_process_instant_major if instant_major else self._lib.tdm_chan_process
-        capi.check(fn(self._h, C.c_void_p(wide.data_ptr()), n, C.c_void_p(out.data_ptr()), out.stride(0) // 2, C.c_void_p(st)),
-                   "tdm_chan_process_instant_major" if instant_major else "tdm_chan_process")
+        # int16 input = TDM_CHAN_IN_CS16 (interleaved int16 pairs, value s / 32768)
+        capi.check(self._lib.tdm_chan_process_ex(self._h, C.c_void_p(wide.data_ptr()), 1 if wide.dtype == torch.int16 else 0, n,
+                                                 C.c_void_p(out.data_ptr()), out.stride(0) // 2, 1 if instant_major else 0, C.c_void_p(st)),
+                   "tdm_chan_process_ex")
         return out
 
     def last_kernel_ms(self):

@@ -74,11 +74,19 @@ double bessel_i0(double x) {
 constexpr int kSlab = 32;
 constexpr int kChanRows = 192;               // rows of the staged window: 192 x 256 B = 48 KB
 __device__ __forceinline__ long long floor_div(long long a, long long b) { return a >= 0 ? a / b : -((-a + b - 1) / b); }
-template <int T>
-__global__ void __launch_bounds__(256) chan_residue_kernel(const float2* __restrict__ in, long long n_in, const float2* __restrict__ hist, long long n_hist,
+// CS16: the capture arrives as interleaved int16 (re, im), what SDR hardware and baseband recordings deliver; sample value
+// = s / 32768 (volk_16i_s32f_convert_32f(.., 32768.0f), src/dsp/osmotetra_dec.h:219 uses the same scale).  Half the
+// bytes from HBM -- and across PCIe when the capture comes from the host.
+__device__ __forceinline__ float2 cs16_to_float2(unsigned v) {
+    return make_float2((float)(short)(v & 0xffffu) * (1.0f / 32768.0f), (float)(short)(v >> 16) * (1.0f / 32768.0f));
+}
+template <int T, bool CS16>
+__global__ void __launch_bounds__(256) chan_residue_kernel(const void* __restrict__ in_raw, long long n_in, const float2* __restrict__ hist, long long n_hist,
                                                            const float* __restrict__ taps, int M, int D, long long n_out, int mi, int period,
                                                            long long t0_global /* global index of in[0] */, float2* __restrict__ u) {
     __shared__ float2 xs[kChanRows * kSlab];
+    const float2* __restrict__ in = reinterpret_cast<const float2*>(in_raw);
+    const unsigned* __restrict__ in16 = reinterpret_cast<const unsigned*>(in_raw);
     const int lane = threadIdx.x & 31, il = threadIdx.x >> 5;
     const int rho0 = blockIdx.y * kSlab, rho = rho0 + lane;
     const long long m0 = (long long)blockIdx.x * mi;
@@ -96,7 +104,7 @@ __global__ void __launch_bounds__(256) chan_residue_kernel(const float2* __restr
         for (int r = il; r < rows; r += 8) {
             const long long idx = (long long)rho + (Jlo + r) * M;            // local sample index: >= 0 new samples, < 0 carried history
             const float2* src = nullptr;
-            if (idx >= 0) { if (idx < n_in) { src = in + idx; } }
+            if (idx >= 0) { if (idx < n_in) { if (CS16) { xs[r * kSlab + lane] = cs16_to_float2(__ldg(in16 + idx)); continue; } src = in + idx; } }
             else if (n_hist + idx >= 0) { src = hist + (n_hist + idx); }
             if (src) { asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(xs0 + (uint32_t)(r * kSlab * 8)), "l"(src) : "memory"); }
             else { xs[r * kSlab + lane] = make_float2(0.f, 0.f); }
@@ -182,10 +190,13 @@ __global__ void __launch_bounds__(256) chan_transpose_kernel(const float2* __res
 }
 
 // the last n_hist samples of [hist | in] become the new history
-__global__ void chan_history_kernel(const float2* __restrict__ in, long long n_in, const float2* __restrict__ hist_old, float2* __restrict__ hist_new, long long n_hist) {
+template <bool CS16>
+__global__ void chan_history_kernel(const void* __restrict__ in_raw, long long n_in, const float2* __restrict__ hist_old, float2* __restrict__ hist_new, long long n_hist) {
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n_hist; i += (long long)gridDim.x * blockDim.x) {
         const long long src = n_in - n_hist + i;              // index into `in`; negative: old history
-        hist_new[i] = src >= 0 ? in[src] : hist_old[n_hist + src];
+        if (src < 0) { hist_new[i] = hist_old[n_hist + src]; }
+        else if (CS16) { hist_new[i] = cs16_to_float2(reinterpret_cast<const unsigned*>(in_raw)[src]); }
+        else { hist_new[i] = reinterpret_cast<const float2*>(in_raw)[src]; }
     }
 }
 
@@ -304,14 +315,20 @@ int tdm_chan_reset(tdm_chan* c) {
     return ok ? TDM_OK : tdm_internal_fail(TDM_ERR_CUDA, "tdm_chan_reset: memset failed");
 }
 
-static int chan_process(tdm_chan* c, const float* wide, int64_t n_wide, float* out, int64_t out_stride, bool instant_major, void* cuda_stream);
+static int chan_process(tdm_chan* c, const void* wide, bool cs16, int64_t n_wide, float* out, int64_t out_stride, bool instant_major, void* cuda_stream);
 int tdm_chan_process(tdm_chan* c, const float* wide, int64_t n_wide, float* out, int64_t out_stride, void* cuda_stream) {
-    return chan_process(c, wide, n_wide, out, out_stride, false, cuda_stream);
+    return chan_process(c, wide, false, n_wide, out, out_stride, false, cuda_stream);
 }
 int tdm_chan_process_instant_major(tdm_chan* c, const float* wide, int64_t n_wide, float* out, int64_t row_pitch, void* cuda_stream) {
-    return chan_process(c, wide, n_wide, out, row_pitch, true, cuda_stream);
+    return chan_process(c, wide, false, n_wide, out, row_pitch, true, cuda_stream);
 }
-static int chan_process(tdm_chan* c, const float* wide, int64_t n_wide, float* out, int64_t out_stride, bool instant_major, void* cuda_stream) {
+int tdm_chan_process_ex(tdm_chan* c, const void* wide, int32_t in_format, int64_t n_wide, float* out, int64_t pitch, int32_t out_layout, void* cuda_stream) {
+    if ((in_format != TDM_CHAN_IN_CF32 && in_format != TDM_CHAN_IN_CS16) || (out_layout != TDM_CHAN_OUT_CHANNEL_MAJOR && out_layout != TDM_CHAN_OUT_INSTANT_MAJOR)) {
+        return tdm_internal_fail(TDM_ERR_ARG, "tdm_chan_process_ex: unknown in_format / out_layout");
+    }
+    return chan_process(c, wide, in_format == TDM_CHAN_IN_CS16, n_wide, out, pitch, out_layout == TDM_CHAN_OUT_INSTANT_MAJOR, cuda_stream);
+}
+static int chan_process(tdm_chan* c, const void* wide, bool cs16, int64_t n_wide, float* out, int64_t out_stride, bool instant_major, void* cuda_stream) {
     if (!c || n_wide < 0 || (n_wide > 0 && (!wide || !out))) { return tdm_internal_fail(TDM_ERR_ARG, "tdm_chan_process: bad arguments"); }
     const int M = c->cfg.n_channels, D = c->cfg.decimation, T = c->cfg.taps_per_branch;
     if (n_wide % D) { return tdm_internal_fail(TDM_ERR_ARG, "tdm_chan_process: n_wide must be a multiple of the decimation %d", D); }
@@ -342,7 +359,7 @@ static int chan_process(tdm_chan* c, const float* wide, int64_t n_wide, float* o
         }
         c->plan_batch = n_out; c->plan_stride = dft_dist;
     }
-    const float2* in = reinterpret_cast<const float2*>(wide);
+    const void* in = wide;
     // instants per CTA: as many as the 192-row window holds (rows = ceil(((mi - 1) D + 31) / M) + T)
     long long mi = ((long long)(kChanRows - T - 1) * M - (kSlab - 1)) / D;
     mi = mi > 1024 ? 1024 : (mi < 8 ? 8 : (mi & ~7LL));
@@ -352,7 +369,7 @@ static int chan_process(tdm_chan* c, const float* wide, int64_t n_wide, float* o
     while (tmp) { const int t = gcd_dm % tmp; gcd_dm = tmp; tmp = t; }
     const int period = (M / gcd_dm <= 64 && M / gcd_dm <= mi / 2) ? M / gcd_dm : 0;     // short branch period: taps-in-registers path
     cudaEventRecord(c->ev[0], st);
-#define TDM_CHAN_LAUNCH(TT) chan_residue_kernel<TT><<<grid, 256, 0, st>>>(in, n_wide, c->d_hist[c->cur], c->n_hist, c->d_taps, M, D, n_out, (int)mi, period, c->t_global, c->d_u)
+#define TDM_CHAN_LAUNCH(TT) if (cs16) { chan_residue_kernel<TT, true><<<grid, 256, 0, st>>>(in, n_wide, c->d_hist[c->cur], c->n_hist, c->d_taps, M, D, n_out, (int)mi, period, c->t_global, c->d_u); } else chan_residue_kernel<TT, false><<<grid, 256, 0, st>>>(in, n_wide, c->d_hist[c->cur], c->n_hist, c->d_taps, M, D, n_out, (int)mi, period, c->t_global, c->d_u)
     switch (T) {
         case 8: TDM_CHAN_LAUNCH(8); break;
         case 12: TDM_CHAN_LAUNCH(12); break;
@@ -371,7 +388,8 @@ static int chan_process(tdm_chan* c, const float* wide, int64_t n_wide, float* o
         chan_transpose_kernel<<<dim3((unsigned)tiles_m, (unsigned)(tiles_k < 65535 ? tiles_k : 65535)), 256, 0, st>>>(c->d_u, reinterpret_cast<float2*>(out), M, n_out, out_stride);
     }
     cudaEventRecord(c->ev[2], st);
-    chan_history_kernel<<<256, 256, 0, st>>>(in, n_wide, c->d_hist[c->cur], c->d_hist[c->cur ^ 1], c->n_hist);
+    if (cs16) { chan_history_kernel<true><<<256, 256, 0, st>>>(in, n_wide, c->d_hist[c->cur], c->d_hist[c->cur ^ 1], c->n_hist); }
+    else { chan_history_kernel<false><<<256, 256, 0, st>>>(in, n_wide, c->d_hist[c->cur], c->d_hist[c->cur ^ 1], c->n_hist); }
     c->cur ^= 1;
     c->t_global += n_wide;
     if (cudaGetLastError() != cudaSuccess) { return leave(tdm_internal_fail(TDM_ERR_CUDA, "tdm_chan_process: kernel launch failed")); }

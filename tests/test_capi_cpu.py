@@ -29,7 +29,7 @@ def test_library_exports_every_declared_symbol(pkg):
     for name in burst:
         assert hasattr(L, name), f"{name} is declared in include/tdm_burst_b200.h but not exported"
     chan = _header_functions("tdm_chan_b200.h")
-    assert len(chan) == 8
+    assert len(chan) == 9
     for name in chan:
         assert hasattr(L, name), f"{name} is declared in include/tdm_chan_b200.h but not exported"
     assert sorted(os.listdir(os.path.join(ROOT, "include"))) == ["tdm_b200.h", "tdm_burst_b200.h", "tdm_chan_b200.h"]

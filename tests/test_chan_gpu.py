@@ -167,3 +167,23 @@ def test_instant_major_output_and_chain(O, pkg, torch_cuda):
         r2 = d2.process(b, dibits=True, instant_major=True)
         torch.cuda.synchronize()
         assert torch.equal(r1.counts, r2.counts) and torch.equal(r1.dibits, r2.dibits)
+
+
+def test_cs16_input_is_the_converted_floats(pkg, torch_cuda):
+    """TDM_CHAN_IN_CS16: interleaved int16 in, taken as s / 32768 -- bit-identical to feeding those floats, in both output
+    layouts, with the formats mixed from call to call (the carried history is floats)."""
+    torch = torch_cuda
+    cfg = pkg.chan_default_config(2)
+    D = cfg.decimation
+    g = torch.Generator(device="cuda").manual_seed(21)
+    raw = torch.randint(-32768, 32768, (D * 900, 2), generator=g, device="cuda", dtype=torch.int32).to(torch.int16)
+    as_float = raw.to(torch.float32) / 32768.0
+    with pkg.Channelizer(cfg) as ch:
+        want = ch.process(as_float)
+        ch.reset()
+        a = ch.process(raw[:D * 300].contiguous())                                  # int16
+        b = ch.process(as_float[D * 300:D * 500].contiguous())                      # float32 in between
+        c = ch.process(raw[D * 500:].contiguous(), instant_major=True)              # int16, the DFT's own layout
+        torch.cuda.synchronize()
+        got = torch.cat([a, b, c.permute(1, 0, 2)], dim=1)
+        assert torch.equal(got, want)

@@ -77,16 +77,16 @@ def measure(args):
         freed = [torch.cuda.Event() for _ in range(2)]
         drained = [torch.cuda.Event() for _ in range(2)]
 
-        def e2e_step():
+        def e2e_step(src_h, stage):
             for k in range(parts):
                 b = k & 1
                 with torch.cuda.stream(copy_s):
                     if k >= 2:
                         copy_s.wait_event(freed[b])
-                    wbuf[b].copy_(wide_h[k * ci * D:(k + 1) * ci * D], non_blocking=True)
+                    stage[b].copy_(src_h[k * ci * D:(k + 1) * ci * D], non_blocking=True)
                     landed[b].record(copy_s)
                 comp_s.wait_event(landed[b])
-                ch.process(wbuf[b], out=obuf, instant_major=True)
+                ch.process(stage[b], out=obuf, instant_major=True)
                 freed[b].record(comp_s)
                 if k >= 2:
                     comp_s.wait_event(drained[b])
@@ -100,12 +100,20 @@ def measure(args):
                     drained[b].record(back_s)
             torch.cuda.synchronize()
 
-        ch.reset(); dm.reset_all()
-        e2e_step()
-        t0 = time.perf_counter()
-        for _ in range(args.steps):
-            e2e_step()
-        e2e_ms = (time.perf_counter() - t0) / args.steps * 1e3
+        def time_e2e(src_h, stage):
+            ch.reset(); dm.reset_all()
+            e2e_step(src_h, stage)
+            t0 = time.perf_counter()
+            for _ in range(args.steps):
+                e2e_step(src_h, stage)
+            return (time.perf_counter() - t0) / args.steps * 1e3
+
+        e2e_ms = time_e2e(wide_h, wbuf)
+        # the same capture as int16 pairs (TDM_CHAN_IN_CS16): what SDR hardware delivers; half the bytes across PCIe
+        wide16_h = torch.empty((n_wide, 2), dtype=torch.int16).pin_memory()
+        wide16_h.copy_((wide.clamp(-3.9, 3.9) * 8192.0).to(torch.int16))
+        wbuf16 = [torch.empty((ci * D, 2), dtype=torch.int16, device=dev) for _ in range(2)]
+        e2e16_ms = time_e2e(wide16_h, wbuf16)
         h2d_bytes = wide_h.numel() * 4
         d2h_bytes = dib_h.numel() + cnt_h.numel() * 4
     try:
@@ -127,7 +135,11 @@ def measure(args):
                 "wideband_msps": round(n_wide / (e2e_ms * 1e-3) / 1e6, 1), "h2d_bytes_per_step": int(h2d_bytes), "d2h_bytes_per_step": int(d2h_bytes),
                 "h2d_gbs": round(h2d_bytes / (e2e_ms * 1e-3) / 1e9, 2),
                 "workload": f"pinned host wideband capture -> H2D -> channeliser -> demodulator -> dibits + counts D2H, {parts} sub-chunks pipelined over three streams; "
-                            f"{8.0 * D / M:.2f} B cross PCIe per channel sample instead of 8 (one wideband stream in instead of {M} channelised float streams)"},
+                            f"{8.0 * D / M:.2f} B cross PCIe per channel sample instead of 8 (one wideband stream in instead of {M} channelised float streams)",
+                "cs16": {"value": round(M * n_out / (e2e16_ms * 1e-3) / 1e6, 1), "unit": "channel Msamples/s", "ms_per_step": round(e2e16_ms, 3),
+                         "h2d_bytes_per_step": int(h2d_bytes // 2), "h2d_gbs": round(h2d_bytes / 2 / (e2e16_ms * 1e-3) / 1e9, 2),
+                         "workload": "the same with the capture as interleaved int16 (TDM_CHAN_IN_CS16, what SDR hardware delivers): "
+                                     f"{4.0 * D / M:.2f} B per channel sample across PCIe"}},
         "chain_channel_msps": round(M * n_out / ((ems + dm_ms) * 1e-3) / 1e6, 1),
         "roofline": {"bound": "hbm", "achieved": round(ach, 1), "peak": peak, "unit": "GB/s", "frac": round(ach / peak, 4), "traffic": None,
                      "peak_source": src, "algorithmic_bytes_per_wideband_sample": round(bytes_per_wide, 2),
