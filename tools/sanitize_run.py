@@ -61,5 +61,19 @@ for (M, D, T) in ((72, 50, 16), (100, 73, 8)):
         whole = ch.process(wide)
         torch.cuda.synchronize()
         assert torch.equal(torch.cat([a, b], dim=1), whole)
+        ch.reset()
+        raw = (wide * 4096).to(torch.int16)                       # CS16 input, the DFT's own output layout
+        im = ch.process(raw, instant_major=True)
+        torch.cuda.synchronize()
+# instant-major input to the demodulator (its own kernel instantiation), full and partial warps
+for variant, cc in ((4, 40), (8, 64), (2, 5)):
+    x = O.generate(cc, 2000)
+    ob2 = O.OracleB(cc)
+    c2, _, d2_, _ = ob2.process(x)
+    with pkg.Demodulator(cc, 2000) as dm:
+        dm.set_kernel_variant(variant)
+        r = dm.process(torch.from_numpy(x).cuda().permute(1, 0, 2).contiguous(), dibits=True, instant_major=True)
+        torch.cuda.synchronize()
+        assert all(np.array_equal(r.dibits[c, :c2[c]].cpu().numpy(), d2_[c, :c2[c]]) for c in range(cc)), variant
 torch.cuda.synchronize()
 print("sanitize_run ok")
