@@ -191,12 +191,68 @@ def test_multi_gpu_example_runs(pkg, tmp_path):
         pytest.skip("no CUDA device")
     exe = _build_sharded_gather(pkg, tmp_path)
     world = min(2, torch.cuda.device_count())
-    # single node: keep NCCL's bootstrap on the loopback interface and off InfiniBand probing (on some boxes the system
-    # libnccl spent two minutes there; the container's hostname may not resolve)
-    env = dict(os.environ, NCCL_SOCKET_IFNAME="lo", NCCL_IB_DISABLE="1")
+    # single node, one or two ranks: keep NCCL's bootstrap on the loopback interface and skip the InfiniBand / NVLS /
+    # multi-node-NVLink probing (on some boxes the system libnccl this plain-C process loads spent two minutes in its
+    # initialisation; the container's hostname may not resolve)
+    env = dict(os.environ, NCCL_SOCKET_IFNAME="lo", NCCL_IB_DISABLE="1", NCCL_NVLS_ENABLE="0", NCCL_MNNVL_ENABLE="0")
     procs = [subprocess.Popen([str(exe), str(r), str(world), str(tmp_path / "id"), "64", "60000"], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, env=env)
              for r in range(world)]
     outs = [p.communicate(timeout=300) for p in procs]
     for p, (o, e) in zip(procs, outs):
         assert p.returncode == 0, (o, e)
     assert f"rank 0 holds {64 * world} channels" in outs[0][0] and " 0 of its own 64 channels differ" in outs[0][0], outs[0][0]
+
+
+def _build_example(pkg, tmp_path, name):
+    import subprocess
+    exe = tmp_path / name
+    libdir = os.path.dirname(pkg.capi.LIB_PATH)
+    cuda = os.environ.get("CUDA_HOME", "/usr/local/cuda")
+    r = subprocess.run(["gcc", "-std=c11", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", os.path.join(ROOT, "include"), "-I", os.path.join(cuda, "include"),
+                        os.path.join(ROOT, "examples", name + ".c"), "-L", libdir, "-ltdm_b200", "-L", os.path.join(cuda, "lib64"), "-lcudart",
+                        f"-Wl,-rpath,{libdir}", f"-Wl,-rpath,{os.path.join(cuda, 'lib64')}", "-o", str(exe)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    return exe
+
+
+def test_wideband_example_builds_and_fails_loudly_without_a_gpu(pkg, tmp_path):
+    """examples/wideband_chain.c: int16 capture -> channeliser -> demodulator from plain C"""
+    import shutil
+    import subprocess
+    import torch
+    if not shutil.which("gcc") or not os.path.exists("/usr/local/cuda/include/cuda_runtime_api.h"):
+        pytest.skip("gcc or the CUDA headers are missing")
+    exe = _build_example(pkg, tmp_path, "wideband_chain")
+    if torch.cuda.is_available():
+        return
+    (tmp_path / "empty.cs16").write_bytes(b"")
+    r = subprocess.run([str(exe), str(tmp_path / "empty.cs16"), "4"], capture_output=True, text=True)
+    assert r.returncode == 3 and "no CPU fallback" in r.stderr, (r.returncode, r.stderr)
+
+
+@pytest.mark.gpu
+def test_wideband_example_finds_the_carriers(O, pkg, tmp_path):
+    """three TETRA carriers on a 144-channel raster, written as an int16 capture file: the C host reports exactly those
+    channels (and no empty one) as locked"""
+    import subprocess
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from oracle import oracle_chan as OC
+    exe = _build_example(pkg, tmp_path, "wideband_chain")
+    M, D, n = 144, 100, 50000
+    carriers = [3, 40, 100]
+    sp = O.default_sg_params(snr_db=60.0, max_freq_off_hz=200.0, min_amp=0.5, max_amp=1.0)
+    nb = O.generate(len(carriers), n, sp)
+    wide = OC.place_on_raster(nb[..., 0] + 1j * nb[..., 1], carriers, M, D)
+    rng = np.random.default_rng(2)
+    wide += 1e-3 * (rng.standard_normal(len(wide)) + 1j * rng.standard_normal(len(wide)))
+    scale = 20000.0 / np.abs(np.concatenate([wide.real, wide.imag])).max()
+    cs16 = np.stack([wide.real, wide.imag], axis=1) * scale
+    np.round(cs16).astype(np.int16).tofile(tmp_path / "capture.cs16")
+    r = subprocess.run([str(exe), str(tmp_path / "capture.cs16"), "4"], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, (r.stdout, r.stderr)
+    locked = sorted(int(line.split()[1]) for line in r.stdout.splitlines() if line.startswith("channel "))
+    assert set(carriers) <= set(locked), r.stdout
+    assert not (set(locked) & {20, 50, 70, 120}), r.stdout
+    assert f"{n * D} wideband samples, {M} channels" in r.stdout
